@@ -1,0 +1,64 @@
+// kernels.cuh — host-side launchers of the sm_100a kernels. One half-iteration of ANLS is, in the reference's
+// vocabulary (src/update_with_missing.cpp:3-55): solve  A ~ Wt' H  for H >= 0, column by column, where
+//   H  is k x ncol (in/out),  Wt is k x len,  A is len x ncol with each column contiguous.
+// Both halves of an iteration use the same launchers with the roles swapped (src/nnmf.cpp:117-119,131-133):
+//   H-half: (H, W,  A   : len = n, ncol = m)      W-half: (W, H, A^T : len = m, ncol = n).
+#pragma once
+#include "common.cuh"
+
+namespace nnlm {
+
+// ---- ingest.cu: upload-time layout conversion (replaces the per-iteration A.t() copy of src/nnmf.cpp:117,131) ----
+struct IngestStats {          // accumulated over chunks, all in fp64 / exact integers
+    double  kl_const_sum;     // sum over finite a of (a+TINY)*log(a+TINY) - a      (src/nnmf.cpp:66-73)
+    int64_t n_missing;        // number of non-finite entries                        (src/nnmf.cpp:64)
+};
+// src: chunk of `jc` columns (col-major, leading dimension len) already on the device.
+// dst_cm (len x ncol, may alias src's parent buffer -> pass nullptr to skip) and dst_rm (ncol x len) receive columns [j0, j0+jc).
+// part: device scratch of at least ingest_part_count(len, jc) * 2 doubles.
+template <typename TOut>
+void launch_ingest(const double* src, int64_t len, int64_t ncol, int64_t j0, int64_t jc, TOut* dst_cm, TOut* dst_rm,
+                   double* part, cudaStream_t st);
+int64_t ingest_part_count(int64_t len, int64_t jc);
+// deterministic fixed-order reduction of `count` partial records of `width` doubles -> out[width]
+void launch_reduce_partials(const double* part, int64_t count, int width, double* out, cudaStream_t st);
+// bit-plane of !isfinite(A) over the column-major linear index + per-column counts (src/update_with_missing.cpp:80-83)
+void launch_na_bits(const double* A, int64_t len, int64_t ncol, uint32_t* bits, int64_t* col_missing, cudaStream_t st);
+// transpose small factor matrices between the R layout (rows x K, col-major) and the device layout (K x rows)
+void launch_transpose_d(const double* in, int64_t rows, int64_t cols, double* out, cudaStream_t st);
+void launch_mask_to_u8_t(const int32_t* in, int64_t rows, int64_t cols, uint8_t* out_t, cudaStream_t st);   // (rows x cols) -> (cols x rows) bytes
+void launch_mask_to_u8(const int32_t* in, int64_t count, uint8_t* out, cudaStream_t st);
+
+// ---- gram.cu: K1/K1r/K6 of SURVEY.md §2.1 ----
+// G = Y Y' (k x k) with the reference's regularisation (src/update_with_missing.cpp:19-24). Y is k x len.
+// part must hold gram_splits(len) * k * k doubles.
+int  gram_splits(int64_t len);
+void launch_gram(const double* Y, int k, int64_t len, const double* pen /*[3] host*/, double* part, double* G, cudaStream_t st);
+// sumW = rowSums(Y) (src/update_with_missing.cpp:27); part must hold gram_splits(len) * k doubles
+void launch_rowsum(const double* Y, int k, int64_t len, double* part, double* out, cudaStream_t st);
+
+// ---- cross_simt.cu: K2 in fp64 on CUDA cores (the "exact" path) ----
+// Qp[s][a + k*j] = sum over the s-th slice of i of Y[a + k*i] * A[i + len*j].   TA = double or float.
+int  cross_simt_splits(int k, int64_t len, int64_t ncol);
+template <typename TA>
+void launch_cross_simt(const double* Y, const TA* A, int k, int64_t len, int64_t ncol, int splits, double* Qp, cudaStream_t st);
+
+// ---- solve_ls.cu: K3/K4/K5 — warp-per-column sequential coordinate descent / Lee multiplicative, square loss ----
+// X (k x ncol) in/out; G regularised Gram (k x k); Qp split-K partials of Wt*A (splits x k x ncol); mask k x ncol bytes or null;
+// l1 = beta(2); sweeps: device counter incremented by the summed sweep count (total_raw_iter).
+void launch_solve_ls(int method, double* X, const double* G, const double* Qp, int splits, const uint8_t* mask,
+                     int k, int64_t ncol, double l1, unsigned max_iter, double rel_tol, unsigned long long* sweeps,
+                     cudaStream_t st);
+
+// ---- error_eval.cu: a8/a9 ----
+// Sums over finite entries of A of (A - W'H)^2 and of -(A+TINY)*log(W'H+TINY) + W'H  (src/nnmf.cpp:121-141).
+// W is k x n, H is k x m, A is n x m. out[0] = sum sq, out[1] = sum kl. part: scratch error_part_count()*2 doubles.
+int64_t error_part_count(int64_t n, int64_t m);
+template <typename TA>
+void launch_error(const TA* A, const double* W, const double* H, int k, int64_t n, int64_t m, double* part, double* out,
+                  cudaStream_t st);
+// out[0] = sum X^2, out[1] = sum X, out[2] = sum_i (sum_a X[a,i])^2 = accu(X*X.t())   (src/nnmf.cpp:224-240)
+int64_t stats_part_count(int64_t cols);
+void launch_factor_stats(const double* X, int k, int64_t cols, double* part, double* out, cudaStream_t st);
+
+}  // namespace nnlm
