@@ -84,6 +84,9 @@ typedef struct nnlm_stats {
     uint64_t d2h_bytes;
     int32_t  precision_used;  /* NNLM_PREC_EXACT or NNLM_PREC_FAST                                 */
     int32_t  reserved0;
+    double gram_ms;           /* device time in the Gram / row-sum / factor re-layout kernels      */
+    uint64_t cross_launches;  /* launches summed into cross_ms (verbose_timing only)               */
+    uint64_t solve_launches;
 } nnlm_stats;
 
 /* ---- c_nnmf (src/nnmf.cpp:4-220) -------------------------------------------------------------
@@ -148,6 +151,16 @@ int nnlm_session_create(nnlm_session** out, const double* A, int64_t n, int64_t 
                         const double* alpha, const double* beta,
                         uint32_t inner_max_iter, double inner_rel_tol, int32_t method,
                         const nnlm_options* opt, char* err, size_t errlen);
+/* Synthetic workload of BASELINE.md §4 generated directly in HBM (the matrix never exists on the host):
+ *   A = u(base+1)(n x K) * u(base+2)(K x m) + noise * u(base+3),  entry NaN iff u(base+4) < na_frac,
+ *   u(seed, idx) = (splitmix64(seed*0x9E3779B97F4A7C15 + idx) >> 11) * 2^-53, idx = i + n*j with j the global column
+ *   (opt->col_offset selects the shard). nnlm_synth_matrix writes the same matrix to host memory. */
+int nnlm_session_create_synthetic(nnlm_session** out, int64_t n, int64_t m, int32_t K, uint64_t seed_base, double noise,
+                                  double na_frac, const double* alpha, const double* beta,
+                                  uint32_t inner_max_iter, double inner_rel_tol, int32_t method,
+                                  const nnlm_options* opt, char* err, size_t errlen);
+int nnlm_synth_matrix(double* A, int64_t n, int64_t m, int32_t k, int64_t col0, uint64_t seed_base, double noise,
+                      double na_frac, char* err, size_t errlen);
 int nnlm_session_set_factors(nnlm_session* s, const double* W, const double* H, char* err, size_t errlen);
 int nnlm_session_get_factors(nnlm_session* s, double* W, double* H, char* err, size_t errlen);
 int nnlm_session_run(nnlm_session* s, uint32_t iters, double* device_ms, int64_t* total_sweeps,
@@ -155,6 +168,7 @@ int nnlm_session_run(nnlm_session* s, uint32_t iters, double* device_ms, int64_t
 /* mse / mkl / target (with penalties) of the resident factors: src/nnmf.cpp:121-149, 224-240 */
 int nnlm_session_error(nnlm_session* s, double* mse, double* mkl, double* target, char* err, size_t errlen);
 int nnlm_session_stats(nnlm_session* s, nnlm_stats* stats);
+int nnlm_session_reset_stats(nnlm_session* s);   /* zero the timing / launch counters */
 void nnlm_session_destroy(nnlm_session* s);
 
 /* ---- multi-GPU plumbing (one process per GPU) ----------------------------------

@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -30,6 +31,14 @@ struct Error : std::runtime_error {
                           cudaGetErrorString(e_), __FILE__, __LINE__, #expr);                           \
             throw ::nnlm::Error(e_ == cudaErrorMemoryAllocation ? NNLM_E_NOMEM : NNLM_E_CUDA, b_);      \
         }                                                                                               \
+    } while (0)
+
+// every kernel launch of this library is followed by NNLM_LAUNCHED(): error check + launch accounting (nnlm_stats.launches)
+inline std::atomic<uint64_t>& launch_counter() { static std::atomic<uint64_t> c{0}; return c; }
+#define NNLM_LAUNCHED()                                                                                 \
+    do {                                                                                                \
+        NNLM_CUDA_CHECK(cudaGetLastError());                                                            \
+        ::nnlm::launch_counter().fetch_add(1, std::memory_order_relaxed);                               \
     } while (0)
 
 #define NNLM_REQUIRE(cond, msg)                                                                         \

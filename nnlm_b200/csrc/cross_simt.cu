@@ -58,7 +58,10 @@ k_cross_simt(const double* __restrict__ Y, const TA* __restrict__ A, int k, int6
         for (int jj = warp; jj < TJ; jj += NT / 32) {
             const int64_t j = j0 + jj;
             double v = 0.0;
-            if (lane < cnt && j < ncol) v = static_cast<double>(A[(i0 + lane) + len * j]);
+            if (lane < cnt && j < ncol) {
+                v = static_cast<double>(A[(i0 + lane) + len * j]);
+                if (is_missing(v)) v = 0.0;      // NA path: the masked cross-product of src/update_with_missing.cpp:91
+            }
             as[lane * AS_LD + jj] = v;
         }
         __syncthreads();
@@ -101,7 +104,7 @@ void launch_one(const double* Y, const TA* A, int k, int64_t len, int64_t ncol, 
     const int64_t per_split = ceil_div(ceil_div(len, splits), TI) * TI;
     dim3 grid((unsigned)ceil_div(ncol, TJ), (unsigned)splits);
     kern<<<grid, 32 * NWJ * NWA, smem, st>>>(Y, A, k, len, ncol, per_split, Qp);
-    NNLM_CUDA_CHECK(cudaGetLastError());
+    NNLM_LAUNCHED();
 }
 
 }  // namespace

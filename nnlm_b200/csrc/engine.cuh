@@ -1,0 +1,133 @@
+// engine.cuh — device-resident state of one ANLS problem and the half-iteration driver.
+//
+// Mirrors the reference's conventions (src/nnmf.cpp:75-98, 109-161): W is held transposed (k x n) for the whole run,
+// both halves go through the same routine with the roles swapped,
+//   W-half: update(W, H, A.t(), Wm, alpha)   (src/nnmf.cpp:117 / :131)
+//   H-half: update(H, W, A,     Hm, beta)    (src/nnmf.cpp:119 / :133)
+// The reference materialises A.t() every iteration; here the transposed copy is made once at upload (ingest.cu) and both
+// copies stay resident in HBM (2 x n*m*elt bytes), so each half streams its own copy with unit stride along the
+// contraction index.
+#pragma once
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace nnlm {
+
+enum class Storage { F64, F32, F16X2 };   // element type of the resident copies of A
+
+struct ErrorTerms {     // raw sums, all fp64
+    double sum_sq;      // sum over finite entries of (A - W'H)^2
+    double sum_kl;      // sum over finite entries of -(A+TINY) log(W'H+TINY) + W'H
+    double w_stats[3];  // sum W^2, sum W, accu(W W')   (src/nnmf.cpp:224-240)
+    double h_stats[3];
+};
+
+// Per-kernel device timing (nnlm_options.verbose_timing): CUDA events recorded on the library's stream around the
+// cross-product and solver launches; accumulated at collect().
+class KernelTimer {
+public:
+    enum Cat { CROSS = 0, SOLVE = 1, GRAM = 2, ERROR = 3, NCAT = 4 };
+    ~KernelTimer();
+    void enable(bool on) { on_ = on; }
+    bool enabled() const { return on_; }
+    void begin(Cat c, cudaStream_t st);
+    void end(cudaStream_t st);
+    void collect();                       // stream must be synchronised
+    double ms[NCAT] = {0, 0, 0, 0};
+    uint64_t count[NCAT] = {0, 0, 0, 0};
+    void reset() { for (int i = 0; i < NCAT; i++) { ms[i] = 0; count[i] = 0; } }
+private:
+    struct Span { cudaEvent_t a, b; Cat c; };
+    std::vector<Span> spans_;
+    std::vector<cudaEvent_t> pool_;
+    cudaEvent_t get();
+    bool on_ = false;
+    Cat cur_ = CROSS;
+    cudaEvent_t cur_a_ = nullptr;
+};
+
+class Engine {
+public:
+    KernelTimer timer;
+    // both_sides = false: only the H-half will run (nnlm_update / nnlm_nnlm), no transposed copy of A is kept
+    Engine(int64_t n, int64_t m, int k, int method, int precision, int device, bool both_sides = true);
+    ~Engine();
+    Engine(const Engine&) = delete;
+    Engine& operator=(const Engine&) = delete;
+
+    // A: n x m column-major host doubles (borrowed for the duration of the call only)
+    void upload_A(const double* A);
+    // A already on the device (n x m column-major fp64); consumed by the same ingest pass
+    void ingest_device_A(const double* dA);
+    void set_factors(const double* W /*n x k*/, const double* H /*k x m*/);
+    void get_factors(double* W, double* H);
+    void set_factors_t(const double* Wt /*k x n*/, const double* H /*k x m*/);
+    void get_H(double* H);
+    // -1: choose like c_nnmf/c_nnlm (NA path iff A has a non-finite entry); 0 / 1: force update() / update_with_missing()
+    void set_missing_mode(int mode) { missing_mode_ = mode; }
+    bool use_missing_path() const { return missing_mode_ < 0 ? n_missing_ > 0 : missing_mode_ != 0; }
+    void set_masks(const int32_t* Wm /*n x k or null*/, const int32_t* Hm /*k x m or null*/);
+    void set_penalties(const double* alpha, const double* beta);
+    void set_inner(unsigned max_iter, double rel_tol) { inner_max_iter_ = max_iter; inner_rel_tol_ = rel_tol; }
+
+    void half_w();      // solve for W given H
+    void half_h();      // solve for H given W
+    // generic single half-iteration on explicit operands already on the device (nnlm_update / nnlm_nnlm)
+    void errors(ErrorTerms* out);                 // synchronises the stream
+    uint64_t take_sweeps();                       // read and reset total_raw_iter (synchronises)
+    void sync();
+
+    int64_t n() const { return n_; }
+    int64_t m() const { return m_; }
+    int k() const { return k_; }
+    int method() const { return method_; }
+    bool any_missing() const { return n_missing_ > 0; }
+    int64_t n_missing() const { return n_missing_; }
+    double kl_const_sum() const { return kl_const_sum_; }
+    int precision_used() const { return storage_ == Storage::F64 ? NNLM_PREC_EXACT : NNLM_PREC_FAST; }
+    cudaStream_t stream() const { return st_; }
+    int device() const { return device_; }
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;
+
+    // direct device access for the single-shot entry points
+    double* dWt() { return Wt_.p; }
+    double* dH() { return H_.p; }
+
+private:
+    struct Half {
+        double* X; int64_t ncol;
+        const double* Y; int64_t len;
+        const void* A;
+        const uint8_t* mask;
+        const double* pen;
+    };
+    void run_half(const Half& h);
+    template <typename TA> void run_half_t(const Half& h);
+    void ensure_scratch();
+
+    int64_t n_, m_;
+    int k_, method_, device_;
+    bool both_sides_;
+    int missing_mode_ = -1;
+    Storage storage_;
+    cudaStream_t st_ = nullptr;
+    unsigned inner_max_iter_ = 50;
+    double inner_rel_tol_ = 1e-9;
+    double alpha_[3] = {0, 0, 0}, beta_[3] = {0, 0, 0};
+
+    DevBuf<double> A64_, At64_;     // n x m and m x n, column-major
+    DevBuf<float> A32_, At32_;
+    DevBuf<double> Wt_, H_;         // k x n, k x m
+    DevBuf<uint8_t> Wm_, Hm_;       // k x n, k x m or empty
+    bool has_wm_ = false, has_hm_ = false;
+    int64_t n_missing_ = 0;
+    double kl_const_sum_ = 0.0;
+
+    // scratch
+    DevBuf<double> gram_part_, G_, Graw_, sumY_, Qp_, Yr_, wh_, red_part_, small_;   // small_: 16 doubles of results
+    DevBuf<unsigned long long> sweeps_;
+    PinnedBuf<double> host_small_;
+};
+
+}  // namespace nnlm

@@ -121,7 +121,7 @@ void launch_error(const TA* A, const double* W, const double* H, int k, int64_t 
     NNLM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)ceil_div(n, ET), (unsigned)ceil_div(m, ET));
     kern<<<grid, 256, smem, st>>>(A, W, H, k, n, m, part);
-    NNLM_CUDA_CHECK(cudaGetLastError());
+    NNLM_LAUNCHED();
     launch_reduce_partials(part, error_part_count(n, m), 2, out, st);
 }
 template void launch_error<double>(const double*, const double*, const double*, int, int64_t, int64_t, double*, double*, cudaStream_t);
@@ -132,7 +132,7 @@ int64_t stats_part_count(int64_t cols) { (void)cols; return STATS_BLOCKS; }
 void launch_factor_stats(const double* X, int k, int64_t cols, double* part, double* out, cudaStream_t st)
 {
     k_factor_stats<<<STATS_BLOCKS, 256, 0, st>>>(X, k, cols, part);
-    NNLM_CUDA_CHECK(cudaGetLastError());
+    NNLM_LAUNCHED();
     launch_reduce_partials(part, STATS_BLOCKS, 3, out, st);
 }
 

@@ -63,13 +63,14 @@ k_gram_partial(const double* __restrict__ Y, int k, int64_t len, int64_t per_spl
 
 // Fixed-order sum of the split partials + the reference's regularisation:
 //   diag += beta0 - beta1 (if they differ); all += beta1 (if non-zero); diag += TINY_NUM   (:20-24)
-__global__ void k_gram_finish(const double* __restrict__ part, int splits, int k, double b0, double b1, double* __restrict__ G)
+__global__ void k_gram_finish(const double* __restrict__ part, int splits, int k, double b0, double b1, int raw, double* __restrict__ G)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= k * k) return;
     double s = 0.0;
     for (int sp = 0; sp < splits; sp++) s += part[(int64_t)sp * k * k + e];
     const bool diag = (e / k) == (e % k);
+    if (raw) { G[e] = s; return; }
     if (b0 != b1 && diag) s += b0 - b1;
     if (b1 != 0.0) s += b1;
     if (diag) s += TINY_NUM;
@@ -129,9 +130,9 @@ void launch_gram(const double* Y, int k, int64_t len, const double* pen, double*
         const unsigned nb = (unsigned)((k + 127) / 128);
         k_gram_partial<8><<<dim3(splits, nb, nb), 256, 0, st>>>(Y, k, len, per_split, part);
     }
-    NNLM_CUDA_CHECK(cudaGetLastError());
-    k_gram_finish<<<(k * k + 255) / 256, 256, 0, st>>>(part, splits, k, pen[0], pen[1], G);
-    NNLM_CUDA_CHECK(cudaGetLastError());
+    NNLM_LAUNCHED();
+    k_gram_finish<<<(k * k + 255) / 256, 256, 0, st>>>(part, splits, k, pen ? pen[0] : 0.0, pen ? pen[1] : 0.0, pen ? 0 : 1, G);
+    NNLM_LAUNCHED();
 }
 
 void launch_rowsum(const double* Y, int k, int64_t len, double* part, double* out, cudaStream_t st)
@@ -140,9 +141,9 @@ void launch_rowsum(const double* Y, int k, int64_t len, double* part, double* ou
     const int splits = gram_splits(len);
     const int64_t per_split = ceil_div(len, splits);
     k_rowsum_partial<<<splits, 256, 256 * sizeof(double), st>>>(Y, k, len, per_split, part);
-    NNLM_CUDA_CHECK(cudaGetLastError());
+    NNLM_LAUNCHED();
     k_rowsum_finish<<<(k + 255) / 256, 256, 0, st>>>(part, splits, k, out);
-    NNLM_CUDA_CHECK(cudaGetLastError());
+    NNLM_LAUNCHED();
 }
 
 }  // namespace nnlm

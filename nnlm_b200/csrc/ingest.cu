@@ -7,6 +7,15 @@ namespace nnlm {
 
 namespace {
 
+// conversion of a stored element: finite doubles beyond the float range saturate instead of becoming infinite, so the
+// set of non-finite (= missing, src/update_with_missing.cpp:80-83) entries is identical in every storage type
+template <typename TOut> __device__ __forceinline__ TOut store_cast(double a);
+template <> __device__ __forceinline__ double store_cast<double>(double a) { return a; }
+template <> __device__ __forceinline__ float store_cast<float>(double a) {
+    if (!is_missing(a) && fabs(a) > 3.4028234663852886e38) return copysignf(3.4028234663852886e38f, (float)a);
+    return static_cast<float>(a);
+}
+
 constexpr int TILE = 32;
 constexpr int ROWS = 8;
 
@@ -29,7 +38,7 @@ k_ingest(const double* __restrict__ src, int64_t len, int64_t ncol, int64_t j0, 
             a = src[i + len * jj];
             if (is_missing(a)) miss += 1.0;
             else kl += (a + TINY_NUM) * log(a + TINY_NUM) - a;
-            if (dst_cm) dst_cm[i + len * (j0 + jj)] = static_cast<TOut>(a);
+            if (dst_cm) dst_cm[i + len * (j0 + jj)] = store_cast<TOut>(a);
         }
         tile[r][tx] = a;
     }
@@ -39,7 +48,7 @@ k_ingest(const double* __restrict__ src, int64_t len, int64_t ncol, int64_t j0, 
 #pragma unroll
         for (int r = ty; r < TILE; r += ROWS) {
             const int64_t ii = i0 + r;
-            if (ii < len && jj < jc) dst_rm[(j0 + jj) + ncol * ii] = static_cast<TOut>(tile[tx][r]);
+            if (ii < len && jj < jc) dst_rm[(j0 + jj) + ncol * ii] = store_cast<TOut>(tile[tx][r]);
         }
     }
     kl = warp_sum(kl);
@@ -156,7 +165,7 @@ void launch_ingest(const double* src, int64_t len, int64_t ncol, int64_t j0, int
     NNLM_REQUIRE(ceil_div(jc, TILE) <= 65535, "ingest chunk has too many columns");
     dim3 grid((unsigned)ceil_div(len, TILE), (unsigned)ceil_div(jc, TILE)), block(TILE, ROWS);
     k_ingest<TOut><<<grid, block, 0, st>>>(src, len, ncol, j0, jc, dst_cm, dst_rm, part);
-    NNLM_CUDA_CHECK(cudaGetLastError());
+    NNLM_LAUNCHED();
 }
 template void launch_ingest<double>(const double*, int64_t, int64_t, int64_t, int64_t, double*, double*, double*, cudaStream_t);
 template void launch_ingest<float>(const double*, int64_t, int64_t, int64_t, int64_t, float*, float*, double*, cudaStream_t);
@@ -164,7 +173,7 @@ template void launch_ingest<float>(const double*, int64_t, int64_t, int64_t, int
 void launch_reduce_partials(const double* part, int64_t count, int width, double* out, cudaStream_t st)
 {
     k_reduce_partials<<<1, 1024, 0, st>>>(part, count, width, out);
-    NNLM_CUDA_CHECK(cudaGetLastError());
+    NNLM_LAUNCHED();
 }
 
 void launch_na_bits(const double* A, int64_t len, int64_t ncol, uint32_t* bits, int64_t* col_missing, cudaStream_t st)
@@ -172,10 +181,10 @@ void launch_na_bits(const double* A, int64_t len, int64_t ncol, uint32_t* bits, 
     const int64_t total = len * ncol;
     if (total <= 0) return;
     k_na_bits<<<grid_for(total, 256), 256, 0, st>>>(A, total, bits);
-    NNLM_CUDA_CHECK(cudaGetLastError());
+    NNLM_LAUNCHED();
     if (col_missing) {
         k_col_missing<<<grid_for(ncol * 32, 256), 256, 0, st>>>(A, len, ncol, col_missing);
-        NNLM_CUDA_CHECK(cudaGetLastError());
+        NNLM_LAUNCHED();
     }
 }
 
@@ -184,21 +193,21 @@ void launch_transpose_d(const double* in, int64_t rows, int64_t cols, double* ou
     if (rows <= 0 || cols <= 0) return;
     dim3 grid((unsigned)ceil_div(rows, TILE), (unsigned)ceil_div(cols, TILE)), block(TILE, ROWS);
     k_transpose_d<<<grid, block, 0, st>>>(in, rows, cols, out);
-    NNLM_CUDA_CHECK(cudaGetLastError());
+    NNLM_LAUNCHED();
 }
 
 void launch_mask_to_u8_t(const int32_t* in, int64_t rows, int64_t cols, uint8_t* out_t, cudaStream_t st)
 {
     if (rows * cols <= 0) return;
     k_mask_u8_t<<<grid_for(rows * cols, 256), 256, 0, st>>>(in, rows, cols, out_t);
-    NNLM_CUDA_CHECK(cudaGetLastError());
+    NNLM_LAUNCHED();
 }
 
 void launch_mask_to_u8(const int32_t* in, int64_t count, uint8_t* out, cudaStream_t st)
 {
     if (count <= 0) return;
     k_mask_u8<<<grid_for(count, 256), 256, 0, st>>>(in, count, out);
-    NNLM_CUDA_CHECK(cudaGetLastError());
+    NNLM_LAUNCHED();
 }
 
 }  // namespace nnlm

@@ -4,6 +4,8 @@
 // Both halves of an iteration use the same launchers with the roles swapped (src/nnmf.cpp:117-119,131-133):
 //   H-half: (H, W,  A   : len = n, ncol = m)      W-half: (W, H, A^T : len = m, ncol = n).
 #pragma once
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace nnlm {
@@ -29,11 +31,18 @@ void launch_transpose_d(const double* in, int64_t rows, int64_t cols, double* ou
 void launch_mask_to_u8_t(const int32_t* in, int64_t rows, int64_t cols, uint8_t* out_t, cudaStream_t st);   // (rows x cols) -> (cols x rows) bytes
 void launch_mask_to_u8(const int32_t* in, int64_t count, uint8_t* out, cudaStream_t st);
 
+// ---- synth.cu: device-side synthetic workload ----
+void launch_uniform(double* out, int64_t count, uint64_t seed, uint64_t offset, double scale, cudaStream_t st);
+// A (n x m local columns [col0, col0+m) of the global matrix) = u(base+1)(n x k) * u(base+2)(k x m_global) + noise*u(base+3);
+// NaN iff u(base+4) < na_frac. Synchronises the stream.
+void launch_synth(double* A, int64_t n, int64_t m, int k, int64_t col0, uint64_t base, double noise, double na_frac,
+                  cudaStream_t st);
+
 // ---- gram.cu: K1/K1r/K6 of SURVEY.md §2.1 ----
 // G = Y Y' (k x k) with the reference's regularisation (src/update_with_missing.cpp:19-24). Y is k x len.
 // part must hold gram_splits(len) * k * k doubles.
 int  gram_splits(int64_t len);
-void launch_gram(const double* Y, int k, int64_t len, const double* pen /*[3] host*/, double* part, double* G, cudaStream_t st);
+void launch_gram(const double* Y, int k, int64_t len, const double* pen /*[3] host, nullptr = raw unregularised Gram*/, double* part, double* G, cudaStream_t st);
 // sumW = rowSums(Y) (src/update_with_missing.cpp:27); part must hold gram_splits(len) * k doubles
 void launch_rowsum(const double* Y, int k, int64_t len, double* part, double* out, cudaStream_t st);
 
@@ -49,6 +58,23 @@ void launch_cross_simt(const double* Y, const TA* A, int k, int64_t len, int64_t
 void launch_solve_ls(int method, double* X, const double* G, const double* Qp, int splits, const uint8_t* mask,
                      int k, int64_t ncol, double l1, unsigned max_iter, double rel_tol, unsigned long long* sweeps,
                      cudaStream_t st);
+
+// ---- solve_ls_missing.cu: K9 + K4/K5, the NA path of the square loss (src/update_with_missing.cpp:58-117) ----
+// Y k x len (the fixed factor), A len x ncol (non-finite = missing), Gfull the raw (unregularised) Gram of Y,
+// Qp the split-K partials of the masked cross-product (missing entries read as zero), pen[3] the penalties.
+template <typename TA>
+void launch_solve_ls_missing(int method, double* X, const double* Y, const TA* A, const double* Gfull, const double* Qp,
+                             int splits, const uint8_t* mask, int k, int64_t len, int64_t ncol, const double* pen,
+                             unsigned max_iter, double rel_tol, unsigned long long* sweeps, cudaStream_t st);
+
+// ---- solve_kl.cu: K7/K8, KL loss, dense and NA (src/base_algorithms.cpp:71-151, update_with_missing.cpp:119-131) ----
+// Yr is the ROW-major copy of the fixed factor: Yr[c*len + i] = Y[c + k*i]; sumY = rowSums(Y) (launch_rowsum).
+int    solve_kl_grid(int64_t ncol);
+size_t solve_kl_scratch_doubles(int64_t len, int64_t ncol);
+template <typename TA>
+void launch_solve_kl(int method, double* X, const double* Yr, const TA* A, const double* sumY, const uint8_t* mask, int k,
+                     int64_t len, int64_t ncol, const double* pen, unsigned max_iter, double rel_tol, int with_missing,
+                     double* wh_scratch, unsigned long long* sweeps, cudaStream_t st);
 
 // ---- error_eval.cu: a8/a9 ----
 // Sums over finite entries of A of (A - W'H)^2 and of -(A+TINY)*log(W'H+TINY) + W'H  (src/nnmf.cpp:121-141).

@@ -1,21 +1,10 @@
-// solve_ls.cu — K3/K4/K5: the per-column non-negative least-squares solvers for the square loss.
-//   method 1: sequential coordinate descent, reference src/base_algorithms.cpp:3-37 (scd_ls_update), preceded by
-//             mu = WtW*H.col(j) - Wt*A.col(j) (+beta2) of src/update_with_missing.cpp:39-41
-//   method 2: Lee-Seung multiplicative rule applied coordinate after coordinate, src/base_algorithms.cpp:40-68
-//
-// One warp per column (columns are independent given Wt: src/update_with_missing.cpp:29-30). Lane l owns rows
-// l, l+32, ... of h and mu in registers; the regularised Gram sits in shared memory, column-major with the row count
-// padded to a multiple of 32 so `mu += d * V[:,c]` is one conflict-free shared load + one DFMA per owned row.
-// The coordinate loop is strictly sequential (each step sees the mu left by the previous one) exactly as the
-// reference; all state is fp64 because the data-dependent control flow (`tmp != Hj(k)`, the relative-change exit)
-// decides the sweep count that is returned as average_epoch.
-//
-// The exit test `rel_err > rel_tol` with rel_err = max_k 2|d|/(new+old+TINY) is evaluated without the division as
-// 2|d| > rel_tol*(new+old+TINY) whenever the denominator is positive (always, for non-negative iterates); this can
-// only differ from the quotient form when the quotient is within one ulp of rel_tol.
+// solve_ls.cu — K3/K4/K5: the per-column non-negative least-squares solvers for the square loss, dense A (one shared
+// regularised Gram for all columns, src/update_with_missing.cpp:17-25). One warp per column (columns are independent
+// given Wt: src/update_with_missing.cpp:29-30); the solver itself is warp_solve_ls in solve_core.cuh.
 #include <algorithm>
 
 #include "kernels.cuh"
+#include "solve_core.cuh"
 
 namespace nnlm {
 
@@ -60,76 +49,7 @@ k_solve_ls(double* __restrict__ X, const double* __restrict__ G, const double* _
             n_masked += __popc(mk[s]);
         }
         if (n_masked == k) continue;                        // src/update_with_missing.cpp:33-34
-
-        unsigned t = 0;
-        bool cont = true;                                   // rel_err starts at 1 + rel_tol
-
-        if (METHOD == 1) {
-            // mu = V h - WtA (+ l1)
-            double mu[RPL];
-#pragma unroll
-            for (int s = 0; s < RPL; s++) mu[s] = 0.0;
-#pragma unroll
-            for (int sc = 0; sc < RPL; sc++) {
-                for (int lc = 0; lc < 32; lc++) {
-                    const int c = 32 * sc + lc;
-                    if (c >= k) break;
-                    const double hc = shfl_d(h[sc], lc);
-#pragma unroll
-                    for (int s = 0; s < RPL; s++) mu[s] = fma(gs[lane + 32 * s + KR * c], hc, mu[s]);
-                }
-            }
-#pragma unroll
-            for (int s = 0; s < RPL; s++) { mu[s] -= q[s]; if (l1 != 0.0) mu[s] += l1; }
-
-            for (; t < max_iter && cont; t++) {
-                bool flag = false;
-#pragma unroll
-                for (int sc = 0; sc < RPL; sc++) {
-                    for (int lc = 0; lc < 32; lc++) {
-                        const int c = 32 * sc + lc;
-                        if (c >= k) break;
-                        if ((mk[sc] >> lc) & 1u) continue;
-                        const double hc = shfl_d(h[sc], lc);
-                        const double muc = shfl_d(mu[sc], lc);
-                        double cand = hc - muc / gs[c + KR * c];
-                        if (cand < 0) cand = 0;
-                        if (cand != hc) {
-                            const double d = cand - hc;
-#pragma unroll
-                            for (int s = 0; s < RPL; s++) mu[s] = fma(d, gs[lane + 32 * s + KR * c], mu[s]);
-                            const double num = 2 * fabs(hc - cand), den = cand + hc + TINY_NUM;
-                            const bool over = (den > 0) ? (num > rel_tol * den) : (num / den > rel_tol);
-                            flag = flag || over;
-                            if (lane == lc) h[sc] = cand;
-                        }
-                    }
-                }
-                cont = flag || (0.0 > rel_tol);
-            }
-        } else {
-            for (; t < max_iter && cont; t++) {
-                bool flag = false;
-#pragma unroll
-                for (int sc = 0; sc < RPL; sc++) {
-                    for (int lc = 0; lc < 32; lc++) {
-                        const int c = 32 * sc + lc;
-                        if (c >= k) break;
-                        if ((mk[sc] >> lc) & 1u) continue;
-                        double part = 0.0;
-#pragma unroll
-                        for (int s = 0; s < RPL; s++) part = fma(gs[lane + 32 * s + KR * c], h[s], part);
-                        const double den = warp_sum(part) + l1;
-                        const double ratio = shfl_d(q[sc], lc) / (den + TINY_NUM);
-                        if (lane == lc) h[sc] *= ratio;
-                        const double e = 2 * fabs(ratio - 1) / (ratio + 1);
-                        flag = flag || (e > rel_tol);
-                    }
-                }
-                cont = flag || (0.0 > rel_tol);
-            }
-        }
-        my_sweeps += t;
+        my_sweeps += warp_solve_ls<RPL, METHOD>(h, q, mk, gs, k, l1, max_iter, rel_tol);
 #pragma unroll
         for (int s = 0; s < RPL; s++) {
             const int r = lane + 32 * s;
@@ -156,7 +76,7 @@ void launch_rpl(int method, double* X, const double* G, const double* Qp, int sp
         NNLM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)blocks, 32 * WARPS, smem, st>>>(X, G, Qp, splits, mask, k, ncol, l1, max_iter, rel_tol, sweeps);
     }
-    NNLM_CUDA_CHECK(cudaGetLastError());
+    NNLM_LAUNCHED();
 }
 
 }  // namespace

@@ -81,10 +81,19 @@ def set_faithful_transpose(on: bool) -> None:
     lib().oracle_set_faithful_transpose(C.c_int(1 if on else 0))
 
 
+def transpose(A, n_threads=0):
+    """A.t() as the reference materialises it each iteration (src/nnmf.cpp:117,131)."""
+    A = np.asfortranarray(A, dtype=np.float64)
+    n, m = A.shape
+    At = np.empty((m, n), dtype=np.float64, order="F")
+    lib().oracle_transpose(_d(A), C.c_int64(n), C.c_int64(m), _d(At), C.c_int32(n_threads))
+    return At
+
+
 def update(H, Wt, A, mask=None, beta=(0.0, 0.0, 0.0), max_iter=10, rel_tol=1e-8, n_threads=1, method=1,
            with_missing=-1):
     """update()/update_with_missing() (src/update_with_missing.cpp). Returns (H_new, total_iter)."""
-    H = _f64(H); Wt = _f64(Wt); A = _f64(A); mk = _mask(mask)
+    H = _f64(H); Wt = np.asfortranarray(Wt, dtype=np.float64); A = np.asfortranarray(A, dtype=np.float64); mk = _mask(mask)
     k, m = H.shape
     n = A.shape[0]
     assert Wt.shape == (k, n) and A.shape == (n, m)

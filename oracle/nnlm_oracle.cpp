@@ -381,6 +381,21 @@ extern "C" {
 
 void oracle_set_faithful_transpose(int on) { g_faithful_transpose = on; }
 
+// Out-of-place transposition At (m x n) = A (n x m)': the copy the reference makes every outer iteration by binding
+// A.t() to a const mat& (src/nnmf.cpp:117,131). Exposed so the CPU baseline can time it with the half-iterations.
+void oracle_transpose(const double* A, int64_t n, int64_t m, double* At, int32_t n_threads)
+{
+    const int nt = resolve_threads(n_threads);
+    constexpr int64_t B = 64;
+    #pragma omp parallel for num_threads(nt) schedule(static) collapse(2)
+    for (int64_t i0 = 0; i0 < n; i0 += B)
+        for (int64_t j0 = 0; j0 < m; j0 += B) {
+            const int64_t i1 = std::min(n, i0 + B), j1 = std::min(m, j0 + B);
+            for (int64_t i = i0; i < i1; i++)
+                for (int64_t j = j0; j < j1; j++) At[j + (size_t)m * i] = A[i + (size_t)n * j];
+        }
+}
+
 int oracle_max_threads(void)
 {
 #ifdef _OPENMP

@@ -1,0 +1,216 @@
+"""GPU parity tests: the CUDA path through the C ABI vs the CPU oracle on identical seeded inputs.
+
+Bar (BASELINE.json north_star): <= 1e-5 relative Frobenius error on W and H at a fixed iteration count
+(rel.tol = -1, the vignette's own trick), bit-exact for the NA mask / indices / sweep counts where the control flow is
+integer. The tolerance used by each test is written next to it.
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+import nnlm_b200
+import oracle
+from nnlm_b200 import _capi as K
+from conftest import umat
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5      # north-star tolerance on W and H (relative Frobenius)
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def synth(n, m, k, noise=0.1, na=0.0, seed=0):
+    A = umat(seed + 1, n, k) @ umat(seed + 2, k, m) + noise * umat(seed + 3, n, m)
+    if na > 0:
+        A[umat(seed + 4, n, m) < na] = np.nan
+    return np.asfortranarray(A)
+
+
+def run_both(A, k, method, T, inner, alpha=(0, 0, 0), beta=(0, 0, 0), Wm=None, Hm=None, precision=K.PREC_EXACT, trace=1):
+    n, m = A.shape
+    W0 = 0.01 * umat(11, n, k); H0 = 0.01 * umat(12, k, m)
+    if Wm is not None:
+        W0[Wm] = 0
+    if Hm is not None:
+        H0[Hm] = 0
+    ref = oracle.nnmf(A, k, W0, H0, Wm=Wm, Hm=Hm, alpha=alpha, beta=beta, max_iter=T, rel_tol=-1, n_threads=0,
+                      inner_max_iter=inner, method=method, trace=trace)
+    loss = "mse" if method < 3 else "mkl"
+    meth = "scd" if method in (1, 3) else "lee"
+    mask = {}
+    if Wm is not None:
+        mask["W"] = Wm
+    if Hm is not None:
+        mask["H"] = Hm
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = nnlm_b200.nnmf(A, k, alpha=alpha, beta=beta, method=meth, loss=loss, init={"W": W0, "H": H0},
+                             mask=mask or None, max_iter=T, rel_tol=-1, trace=trace, inner_max_iter=inner,
+                             check_k=False, precision=precision)
+    return ref, got
+
+
+@pytest.mark.parametrize("method,inner", [(1, 50), (2, 50), (3, 1), (4, 1), (3, 4), (4, 3)])
+@pytest.mark.parametrize("T", [1, 5, 20])
+def test_nnmf_dense_parity(method, inner, T):
+    A = synth(300, 120, 6)
+    ref, got = run_both(A, 6, method, T, inner)
+    assert got.n_iteration == ref["n_iteration"] == T
+    assert rel(got.W, ref["W"]) < TOL and rel(got.H, ref["H"]) < TOL
+    np.testing.assert_allclose(got.mse, ref["mse"], rtol=1e-7)
+    np.testing.assert_allclose(got.mkl, ref["mkl"], rtol=1e-7, atol=1e-12)
+    np.testing.assert_allclose(got.target_loss, ref["target_loss"], rtol=1e-7)
+    # sweep counts are integers decided by fp64 control flow; allow rare one-ulp flips of the exit test
+    np.testing.assert_allclose(got.average_epochs, ref["average_epochs"], rtol=2e-3)
+    assert got.stats["launches"] > 0
+
+
+@pytest.mark.parametrize("method,inner", [(1, 50), (2, 50), (3, 1), (4, 1)])
+def test_nnmf_missing_parity(method, inner):
+    A = synth(260, 90, 5, na=0.2)
+    assert np.isnan(A).sum() > 0
+    ref, got = run_both(A, 5, method, 5, inner)
+    assert rel(got.W, ref["W"]) < TOL and rel(got.H, ref["H"]) < TOL
+    np.testing.assert_allclose(got.mse, ref["mse"], rtol=1e-7)
+    np.testing.assert_allclose(got.mkl, ref["mkl"], rtol=1e-7, atol=1e-12)
+
+
+def test_nnmf_missing_mostly_empty_columns():
+    # columns with more than half of the entries missing take the "direct" Gram branch; one column is complete
+    A = synth(200, 40, 4, na=0.7)
+    A[:, 3] = synth(200, 40, 4)[:, 3]
+    ref, got = run_both(A, 4, 1, 4, 50)
+    assert rel(got.W, ref["W"]) < TOL and rel(got.H, ref["H"]) < TOL
+
+
+@pytest.mark.parametrize("method,inner", [(1, 50), (2, 20), (3, 2), (4, 2)])
+def test_nnmf_regularised_and_masked(method, inner):
+    rng = np.random.default_rng(5)
+    n, m, k = 150, 70, 5
+    A = synth(n, m, k)
+    Wm = rng.random((n, k)) < 0.2
+    Hm = rng.random((k, m)) < 0.1
+    Hm[:, 7] = True                                    # a fully masked column is skipped (update_with_missing.cpp:33-34)
+    ref, got = run_both(A, k, method, 6, inner, alpha=(0.02, 0.01, 0.005), beta=(0.01, 0.0, 0.01), Wm=Wm, Hm=Hm)
+    assert (got.W[Wm] == 0).all() and (got.H[Hm] == 0).all()
+    assert rel(got.W, ref["W"]) < TOL and rel(got.H, ref["H"]) < TOL
+    np.testing.assert_allclose(got.target_loss, ref["target_loss"], rtol=1e-7)
+
+
+def test_nnmf_k_up_to_128():
+    A = synth(400, 300, 100)
+    ref, got = run_both(A, 100, 1, 3, 50)
+    assert rel(got.W, ref["W"]) < TOL and rel(got.H, ref["H"]) < TOL
+
+
+def test_nnmf_nsclc_config1(nsclc):
+    """BASELINE.json configs[0]: nnmf(nsclc, k=3, 'scd', 'mse') with the R defaults (R/nnmf.R:136-141)."""
+    n, m = nsclc.shape
+    W0 = 0.01 * umat(11, n, 3); H0 = 0.01 * umat(12, 3, m)
+    ref = oracle.nnmf(nsclc, 3, W0, H0, max_iter=500, rel_tol=1e-4, inner_max_iter=50, inner_rel_tol=1e-9, method=1, trace=2)
+    got = nnlm_b200.nnmf(nsclc, 3, init={"W": W0, "H": H0}, precision=K.PREC_EXACT)
+    assert got.n_iteration == ref["n_iteration"]
+    assert got.converged and ref["converged"]
+    assert (got.W >= 0).all() and (got.H >= 0).all()
+    assert rel(got.W, ref["W"]) < TOL and rel(got.H, ref["H"]) < TOL
+    np.testing.assert_allclose(got.target_loss, ref["target_loss"], rtol=1e-8)
+    assert np.all(np.diff(got.target_loss) <= 1e-12 * got.target_loss[:-1])
+
+
+def test_nnlm_golden_vector_on_gpu():
+    """tests/testthat/test-nnlm.R:29-43 through the CUDA path."""
+    A2 = np.array([0.735, -1.428, 0.619, -0.006, -0.686, -0.279, -0.783, -0.779,
+                   -0.375, -0.319, 0.085, -0.768, -0.626, -0.901, 0.664, 0.3,
+                   0.075, 0.206, -0.489, -0.628, -0.047, 0.163, 1.292, -0.464,
+                   0.305, -0.084, 0.41, 0.184, 1.779, 0.038, 1.176, -0.559,
+                   -0.946, -0.665, 0.452, 0.527, -0.23, 1.397, 1.764, 0.486]).reshape((8, 5), order="F")
+    b3 = np.array([1.0, -3, 2, 0, 4])
+    sol = nnlm_b200.nnlm(A2, A2 @ b3, precision=K.PREC_EXACT)
+    golden = np.array([0.649015454583225, 0, 0.338999499138442, 0.810422082985878, 3.94571883712895])
+    np.testing.assert_allclose(sol.coefficients, golden, rtol=0, atol=1.5e-8)
+
+
+def test_nnlm_exact_recovery_on_gpu():
+    A1 = np.array([1.883, 1.237, 0.274, 1.916, 0.807, 0.375, 2.135, 3.237, 0.706, 0.056, 3.405, 0.874, 1.511, 1.162, 4.325,
+                   1.843, 0.751, 0.099, 0.126, 0.208, 0.133, 0.738, 0.378, 0.741, 0.96, 2.101, 2.155, 0.481, 2.187,
+                   0.165]).reshape((6, 5), order="F")
+    b = np.array([1.0, 2, 3, 4, 0])
+    sol = nnlm_b200.nnlm(A1, A1 @ b, precision=K.PREC_EXACT)
+    np.testing.assert_allclose(sol.coefficients, b, rtol=0, atol=1.5e-8)
+    b2 = np.array([1.0, 0, 2, 4, 0, 8, 0, 3, 6, 2]).reshape((5, 2), order="F")
+    sol2 = nnlm_b200.nnlm(A1, A1 @ b2, precision=K.PREC_EXACT)
+    np.testing.assert_allclose(sol2.coefficients, b2, rtol=0, atol=1.5e-8)
+
+
+@pytest.mark.parametrize("method", [1, 2, 3, 4])
+@pytest.mark.parametrize("with_missing", [0, 1])
+def test_update_half_iteration_parity(method, with_missing):
+    n, m, k = 500, 64, 9
+    Wt = umat(1, k, n); A = synth(n, m, k, seed=20); H0 = umat(3, k, m)
+    if with_missing:
+        A[umat(9, n, m) < 0.15] = np.nan
+    inner = 7 if method < 3 else 2
+    href, tref = oracle.update(H0, Wt, A, method=method, max_iter=inner, rel_tol=1e-9, with_missing=with_missing, n_threads=0)
+    hgot, tgot = nnlm_b200.nnlm_update(H0, Wt, A, method=method, max_iter=inner, rel_tol=1e-9, with_missing=with_missing,
+                                       precision=K.PREC_EXACT)
+    assert rel(hgot, href) < 1e-9
+    assert tgot == tref           # integer sweep count
+
+
+def test_na_mask_bit_exact():
+    rng = np.random.default_rng(3)
+    n, m = 1237, 61
+    A = rng.random((n, m))
+    A[rng.random((n, m)) < 0.2] = np.nan
+    A[5, 7] = np.inf; A[6, 7] = -np.inf
+    A = np.asfortranarray(A)
+    bits, cols = nnlm_b200.na_mask(A)
+    expect = ~np.isfinite(A.ravel(order="F"))
+    pad = (-len(expect)) % 32
+    packed = np.packbits(np.concatenate([expect, np.zeros(pad, bool)]).reshape(-1, 32)[:, ::-1], axis=1)
+    words = packed.view(">u4").ravel().astype(np.uint32)
+    assert np.array_equal(bits, words)
+    assert np.array_equal(cols, (~np.isfinite(A)).sum(axis=0))
+
+
+def test_warning_text_and_interrupt():
+    A = synth(60, 30, 3)
+    with pytest.warns(RuntimeWarning, match="Target tolerance not reached. Try a larger max.iter."):
+        nnlm_b200.nnmf(A, 2, alpha=0.1, max_iter=10, precision=K.PREC_EXACT)
+    calls = []
+    with pytest.raises(K.Interrupted):
+        nnlm_b200.nnmf(A, 2, max_iter=50, rel_tol=-1, interrupt=lambda: (calls.append(1), len(calls) > 3)[1],
+                       precision=K.PREC_EXACT)
+    assert len(calls) == 4
+
+
+def test_rank3_reconstruction_properties():
+    """tests/testthat/test-nnmf.R:5-24 on the GPU: exact rank-3 product is reconstructed by all four variants."""
+    A = np.asfortranarray(umat(234, 50, 3) @ umat(235, 3, 10))
+    for method, loss, mi, rt, tol in [("scd", "mse", 10000, 1e-8, 1.5e-8), ("scd", "mkl", 2000, 1e-8, 1e-6),
+                                      ("lee", "mse", 10000, 1e-8, 1e-6), ("lee", "mkl", 10000, 1e-6, 1e-3)]:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            r = nnlm_b200.nnmf(A, 3, method=method, loss=loss, max_iter=mi, rel_tol=rt, rng=np.random.default_rng(123),
+                               precision=K.PREC_EXACT)
+        assert (r.W >= 0).all() and (r.H >= 0).all()
+        assert np.mean(np.abs(r.W @ r.H - A)) / np.mean(np.abs(A)) < tol, (method, loss)
+
+
+def test_session_matches_nnmf():
+    A = synth(300, 200, 8)
+    W0 = 0.01 * umat(11, 300, 8); H0 = 0.01 * umat(12, 8, 200)
+    ref = oracle.nnmf(A, 8, W0, H0, max_iter=6, rel_tol=-1, inner_max_iter=50, method=1, trace=999999, n_threads=0)
+    with nnlm_b200.Session(A, k=8, method=1, precision=K.PREC_EXACT) as s:
+        s.set_factors(W0, H0)
+        ms, sweeps = s.run(6)
+        W, H = s.get_factors()
+        mse, mkl, tgt = s.error()
+        assert s.stats()["launches"] > 0
+    assert ms > 0 and sweeps > 0
+    assert rel(W, ref["W"]) < TOL and rel(H, ref["H"]) < TOL
+    assert mse == pytest.approx(ref["mse"][-1], rel=1e-8)
