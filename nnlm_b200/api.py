@@ -247,7 +247,7 @@ def nnlm(x, y, alpha=(0.0, 0.0, 0.0), method="scd", loss="mse", init=None, mask=
     n, p = x.shape
     q = y2.shape[1]
     if check_x:
-        if n < p or np.linalg.cond(x, 1) > 1.0 / np.finfo(np.float64).eps:
+        if n < p or np.linalg.cond(x) > 1.0 / np.finfo(np.float64).eps:         # R: rcond(x) < .Machine$double.eps
             warnings.warn("x does not have a full column rank. Solution may not be unique.", RuntimeWarning, stacklevel=2)
     alpha = K.vec3(alpha)
     if show_warning and alpha[0] < alpha[1]:
