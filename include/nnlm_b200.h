@@ -138,6 +138,12 @@ int nnlm_update(double* H, const double* Wt, const double* A, const int32_t* mas
                 const nnlm_options* opt, nnlm_stats* stats,
                 char* err, size_t errlen);
 
+/* ---- diagnostic: the cross-product Q = Wt * A (k x m) alone — the contraction `Wt * A.col(j)` of
+ * src/update_with_missing.cpp:39,45 for all columns — through the kernels a half-iteration uses (opt->precision selects
+ * the fp64 CUDA-core or the tcgen05 path). Non-finite entries of A are read as zero (the masked product of :91). */
+int nnlm_cross(const double* Wt, const double* A, int32_t k, int64_t n, int64_t m, double* Q,
+               const nnlm_options* opt, nnlm_stats* stats, char* err, size_t errlen);
+
 /* ---- device-resident session: the benchmark's "inputs already in HBM" path -------------------
  * nnlm_session_create uploads A once (the copy + layout conversion c_nnmf implies per call);
  * nnlm_session_run performs `iters` ANLS iterations (W-half then H-half, src/nnmf.cpp:109-161 without the

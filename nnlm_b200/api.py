@@ -321,3 +321,19 @@ def na_mask(A):
                               cols.ctypes.data_as(C.POINTER(C.c_int64)), err, C.c_size_t(512))
     K.check(rc, err)
     return bits, cols
+
+
+def cross(Wt, A, *, precision=K.PREC_AUTO, device=-1):
+    """Diagnostic: Q = Wt @ A (non-finite entries of A read as zero) through the library's cross-product kernels."""
+    Wt = K.f64(Wt, copy=False); A = K.f64(A, copy=False)
+    k, n = Wt.shape
+    m = A.shape[1]
+    assert A.shape[0] == n
+    Q = np.empty((k, m), dtype=np.float64, order="F")
+    err = C.create_string_buffer(512)
+    opt = _options(precision, device)
+    st = K.Stats()
+    rc = K.lib().nnlm_cross(K.d(Wt), K.d(A), C.c_int32(k), C.c_int64(n), C.c_int64(m), K.d(Q), C.byref(opt), C.byref(st),
+                            err, C.c_size_t(512))
+    K.check(rc, err)
+    return Q, st.as_dict()

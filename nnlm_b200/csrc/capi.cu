@@ -3,6 +3,7 @@
 // the benchmark. All arithmetic happens in the kernels driven by Engine; this file is bookkeeping.
 #include <cmath>
 #include <memory>
+#include <vector>
 
 #include "engine.cuh"
 
@@ -225,12 +226,12 @@ int nnlm_update(double* H, const double* Wt, const double* A, const int32_t* mas
         if (stats) std::memset(stats, 0, sizeof *stats);
         const uint64_t launches0 = launch_counter().load();
         Engine eng(n, m, k, method, precision_of(opt, n, m), opt ? opt->device : -1, /*both_sides=*/false);
+        eng.set_missing_mode(with_missing);
         eng.upload_A(A);
         eng.set_factors_t(Wt, H);
         eng.set_masks(nullptr, mask);
         eng.set_penalties(nullptr, beta);
         eng.set_inner(max_iter, rel_tol);
-        eng.set_missing_mode(with_missing);
         eng.half_h();
         const uint64_t t = eng.take_sweeps();
         eng.get_H(H);
@@ -264,6 +265,26 @@ int nnlm_nnlm(const double* x, const double* y, int64_t n, int64_t p, int64_t q,
         const uint64_t t = eng.take_sweeps();
         eng.get_H(coef);
         if (n_iteration) *n_iteration = (int64_t)t;
+        fill_stats(stats, eng, launches0);
+        return NNLM_OK;
+    });
+}
+
+// diagnostic entry: the cross-product Q = Wt * A alone (the contraction the reference forms per column,
+// src/update_with_missing.cpp:39), through the same kernels a half-iteration uses
+int nnlm_cross(const double* Wt, const double* A, int32_t k, int64_t n, int64_t m, double* Q,
+               const nnlm_options* opt, nnlm_stats* stats, char* err, size_t errlen)
+{
+    return guarded(err, errlen, [&]() -> int {
+        NNLM_REQUIRE(Wt && A && Q && k > 0 && n > 0 && m > 0, "nnlm_cross: bad argument");
+        if (stats) std::memset(stats, 0, sizeof *stats);
+        const uint64_t launches0 = launch_counter().load();
+        Engine eng(n, m, k, NNLM_SCD_MSE, precision_of(opt, n, m), opt ? opt->device : -1, /*both_sides=*/false);
+        eng.set_missing_mode(0);
+        eng.upload_A(A);
+        std::vector<double> H0((size_t)k * m, 0.0);
+        eng.set_factors_t(Wt, H0.data());
+        eng.cross_only(Q);
         fill_stats(stats, eng, launches0);
         return NNLM_OK;
     });

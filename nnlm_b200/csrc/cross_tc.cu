@@ -1,0 +1,600 @@
+// cross_tc.cu — K2 on the 5th-generation tensor cores: the cross-product  Q = Wt * A  (k x ncol) of one half-iteration,
+// which the reference forms one column at a time as `Wt * A.col(j)` (src/update_with_missing.cpp:39,45), as ONE
+// HBM-bound pass over the resident copy of A.
+//
+// Precision. The reference is fp64; the parity bound is 1e-5 on W and H. A and the fixed factor are each stored as two
+// fp16 planes, x*s = hi + lo*2^-11 (s a power of two, 22-24 significant bits, the same 4 bytes per element of A as fp32):
+//     sum_i A[i,j] F[a,i]  =  ( sum hi_A hi_F  +  2^-11 * sum (hi_A lo_F + lo_A hi_F) ) / (s_A s_F[a])      (+ O(2^-22) dropped)
+// Each product of two fp16 values is exact in the fp32 accumulator; the two sums live in separate TMEM accumulators so
+// the small terms are not rounded against the large ones. Long fp32 accumulation is avoided (the tensor core truncates
+// each accumulate, which biases long sums): every `drain` k-blocks (default 16 = 1024 contraction indices) the accumulators are read out of TMEM and added into fp64 registers, while the tensor core
+// continues into the other TMEM buffer. Measured error of the whole cross-product vs fp64: see tests/test_gpu_cross.py.
+//
+// Centering. The tensor core truncates every accumulate; with all-positive data that is a systematic bias (measured:
+// -1.2e-6 relative at 256 indices per drain, -1.6e-5 at 4096). The planes therefore hold A minus its column mean,
+// A'[i,j] = A[i,j] - c[j], whose products have mixed signs (accumulators stay small, truncation is unbiased), and the
+// mean component is added back exactly in fp64:  sum_i A[i,j] F[a,i] = sum_i A'[i,j] F[a,i] + c[j] * rowsum(F)[a].
+//
+// Mapping (UMMA D[M x N] = A[M x K] * B[N x K]^T, both operands K-major, SWIZZLE_128B):
+//   M = 128 columns j of A   (operand rows = columns of the matrix, contiguous along the contraction index i)
+//   N = NP  = k padded to 32/64   (rows a of the factor, row-major copy made by split_factor)
+//   K = 64 fp16 (= one 128-byte swizzle row) per pipeline stage, UMMA_K = 16 -> 4 k-steps x 3 products per stage
+// Work = (tile, k-block) units in tile-major order, cut into gridDim.x equal contiguous ranges (stream-K): every CTA
+// streams the same number of bytes; a tile shared by several CTAs receives one fp64 partial per CTA in slot order
+// (deterministic), summed by the solver exactly like the split-K partials of the fp64 path.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocation), warps 2..9 = epilogue (TMEM -> fp64).
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace nnlm {
+
+namespace {
+
+constexpr int BM = 128;          // columns of A per tile
+constexpr int BK = 64;           // fp16 elements per k-block (128 bytes)
+constexpr int DRAIN_DEFAULT = 16; // k-blocks between TMEM drains (1024 contraction indices = 64 MMAs per accumulator)
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 32 * (2 + EPI_WARPS);
+constexpr float LO_SCALE = 2048.0f;            // 2^11
+constexpr double LO_UNSCALE = 1.0 / 2048.0;
+
+// ---------------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], fp16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major SWIZZLE_128B operand descriptor: 8-row groups 1024 bytes apart (SBO), version 1 (sm_100), layout type 2
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;                  // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset
+    d |= (uint64_t)1 << 46;                  // descriptor version
+    d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+    return d;
+}
+
+template <int N> struct TmemLd;
+template <> struct TmemLd<16> {
+    __device__ static __forceinline__ void ld(uint32_t taddr, uint32_t (&r)[16]) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                     : "r"(taddr));
+    }
+};
+template <> struct TmemLd<32> {
+    __device__ static __forceinline__ void ld(uint32_t taddr, uint32_t (&r)[32]) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                     "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                       "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                     : "r"(taddr));
+    }
+};
+
+struct CrossParams {
+    int64_t ncol;          // columns of A (rows of the UMMA M operand)
+    int64_t kblocks;       // ceil(len / BK)
+    int64_t units;         // tiles * kblocks
+    int k;                 // true rank
+    double* Qp;            // [slots][ncol][k]
+    const double* unscale; // [NP]: 1 / (s_A * s_F[a])
+    int drain;             // k-blocks accumulated in TMEM between two drains into the fp64 registers
+    const double* center;  // [ncol] mean of each column of A that was subtracted before the split (or nullptr)
+    const double* fsum;    // [k] row sums of the factor
+};
+
+// first CTA whose unit range [floor(c*U/P), floor((c+1)*U/P)) reaches unit `u`
+__host__ __device__ inline int64_t first_cta_of_unit(int64_t u, int64_t U, int64_t P) {
+    int64_t c = (u * P) / U;
+    while (c + 1 < P && ((c + 1) * U) / P <= u) c++;
+    while (c > 0 && (c * U) / P > u) c--;
+    return c;
+}
+
+template <int NP, int STAGES>
+__global__ void __launch_bounds__(THREADS, 1)
+k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+           const __grid_constant__ CUtensorMap mapF_hi, const __grid_constant__ CUtensorMap mapF_lo, const CrossParams p)
+{
+    constexpr int A_BYTES = BM * BK * 2;                   // 16 KB per plane per stage
+    constexpr int F_BYTES = NP * BK * 2;
+    constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * F_BYTES;
+    constexpr int CPT = NP / 2;                            // accumulator columns per epilogue thread
+    constexpr uint32_t TMEM_COLS = (4 * NP <= 128) ? 128 : (4 * NP <= 256 ? 256 : 512);
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // f16 x f16 -> f32, K-major
+
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B operand tiles need 1024-byte alignment: align by hand (the launch reserves the slack)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* tiles = smem;                                                   // STAGES * STAGE_BYTES
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tfull = empty + STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t P = gridDim.x, U = p.units, KBn = p.kblocks;
+    const int64_t u0 = ((int64_t)blockIdx.x * U) / P, u1 = ((int64_t)(blockIdx.x + 1) * U) / P;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================== TMA producer =====================================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t u = u0; u < u1; u++) {
+                const int64_t tile = u / KBn, kb = u % KBn;
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* sa = tiles + stage * STAGE_BYTES;
+                mbar_expect_tx(&full[stage], STAGE_BYTES);
+                const int c0 = (int)(kb * BK), c1 = (int)(tile * BM);
+                tma_load_2d(sa, &mapA_hi, &full[stage], c0, c1);
+                tma_load_2d(sa + A_BYTES, &mapA_lo, &full[stage], c0, c1);
+                tma_load_2d(sa + 2 * A_BYTES, &mapF_hi, &full[stage], c0, 0);
+                tma_load_2d(sa + 2 * A_BYTES + F_BYTES, &mapF_lo, &full[stage], c0, 0);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =====================================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            uint32_t chunk = 0;                       // running drain-chunk counter of this CTA
+            int64_t u = u0;
+            while (u < u1) {
+                const int64_t tile = u / KBn;
+                const int64_t seg_end = min(u1, (tile + 1) * KBn);
+                while (u < seg_end) {
+                    const int64_t chunk_end = min(seg_end, u + (int64_t)p.drain);
+                    const uint32_t buf = chunk & 1, tph = (chunk >> 1) & 1;
+                    mbar_wait(&tempty[buf], tph ^ 1);           // epilogue has drained this TMEM buffer
+                    tc_fence_after();
+                    const uint32_t d0 = tmem_base + buf * (2 * NP), d1 = d0 + NP;
+                    bool first = true;
+                    for (; u < chunk_end; u++) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(tiles + stage * STAGE_BYTES);
+                        const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_BYTES);
+                        const uint64_t f_hi = make_desc(sa + 2 * A_BYTES), f_lo = make_desc(sa + 2 * A_BYTES + F_BYTES);
+#pragma unroll
+                        for (int ks = 0; ks < BK / 16; ks++) {
+                            const uint64_t adv = (uint64_t)((ks * 32) >> 4);     // 16 fp16 = 32 bytes along K
+                            const uint32_t acc = (first && ks == 0) ? 0u : 1u;
+                            umma_f16(d0, a_hi + adv, f_hi + adv, IDESC, acc);    // hi*hi
+                            umma_f16(d1, a_hi + adv, f_lo + adv, IDESC, acc);    // hi*lo
+                            umma_f16(d1, a_lo + adv, f_hi + adv, IDESC, 1u);     // lo*hi
+                        }
+                        first = false;
+                        tc_commit(&empty[stage]);               // frees the smem stage when these MMAs retire
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    tc_commit(&tfull[buf]);                     // accumulators of this chunk are complete
+                    chunk++;
+                }
+            }
+        }
+    } else {
+        // ===================================== epilogue: TMEM -> fp64 registers -> partial tile =====================================
+        const int ew = warp - 2;
+        const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+        const int half = ew >> 2;                     // which half of the NP accumulator columns
+        const int row = quarter * 32 + lane;          // row of the tile = column of A
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        uint32_t chunk = 0;
+        int64_t u = u0;
+        while (u < u1) {
+            const int64_t tile = u / KBn;
+            const int64_t seg_end = min(u1, (tile + 1) * KBn);
+            double acc[CPT];
+#pragma unroll
+            for (int c = 0; c < CPT; c++) acc[c] = 0.0;
+            while (u < seg_end) {
+                const int64_t chunk_end = min(seg_end, u + (int64_t)p.drain);
+                const uint32_t buf = chunk & 1, tph = (chunk >> 1) & 1;
+                mbar_wait(&tfull[buf], tph);
+                tc_fence_after();
+                uint32_t r0[CPT], r1[CPT];
+                const uint32_t t0 = tmem_base + lane_addr + buf * (2 * NP) + half * CPT;
+                TmemLd<CPT>::ld(t0, r0);
+                TmemLd<CPT>::ld(t0 + NP, r1);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[buf]);       // buffer may be overwritten by the next-but-one chunk
+#pragma unroll
+                for (int c = 0; c < CPT; c++)
+                    acc[c] += (double)__uint_as_float(r0[c]) + (double)__uint_as_float(r1[c]) * LO_UNSCALE;
+                u = chunk_end;
+                chunk++;
+            }
+            // partial tile -> slot (index of this CTA among the CTAs that touch the tile)
+            const int64_t slot = (int64_t)blockIdx.x - first_cta_of_unit(tile * KBn, U, P);
+            const int64_t j = tile * BM + row;
+            if (j < p.ncol) {
+                double* out = p.Qp + (slot * p.ncol + j) * p.k;
+                const double cj = (slot == 0 && p.center != nullptr) ? p.center[j] : 0.0;    // mean component, added once
+#pragma unroll
+                for (int c = 0; c < CPT; c++) {
+                    const int a = half * CPT + c;
+                    if (a < p.k) out[a] = fma(cj, p.fsum[a], acc[c] * p.unscale[a]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- operand preparation
+// |x| maxima as fp64 bit patterns (non-negative doubles order like unsigned integers)
+__global__ void k_rowmax(const double* __restrict__ F, int k, int64_t len, unsigned long long* __restrict__ rowmax)
+{
+    extern __shared__ unsigned long long smx[];       // [k]
+    for (int a = threadIdx.x; a < k; a += blockDim.x) smx[a] = 0ull;
+    __syncthreads();
+    const int64_t total = (int64_t)k * len;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const double v = fabs(F[e]);
+        if (!is_missing(v)) atomicMax(&smx[e % k], (unsigned long long)__double_as_longlong(v));
+    }
+    __syncthreads();
+    for (int a = threadIdx.x; a < k; a += blockDim.x) if (smx[a]) atomicMax(&rowmax[a], smx[a]);
+}
+
+// power-of-two scale that brings `maxabs` into [2^13, 2^14): fp16 keeps 11 significant bits there and the scaled
+// remainder (< 2^3 before the 2^11 lift) stays far from both overflow and the subnormal range
+__device__ __forceinline__ double pow2_scale(double maxabs)
+{
+    if (!(maxabs > 0.0)) return 1.0;
+    int e;
+    frexp(maxabs, &e);                 // maxabs = f * 2^e, f in [0.5, 1)
+    return ldexp(1.0, 14 - e);
+}
+
+// scales[a] = s_F[a]; unscale[a] = 1 / (s_A * s_F[a])
+__global__ void k_make_scales(const unsigned long long* __restrict__ rowmax, int k, int np, const double* __restrict__ sA,
+                              double* __restrict__ scales, double* __restrict__ unscale)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= np) return;
+    const double s = (a < k) ? pow2_scale(__longlong_as_double((long long)rowmax[a])) : 1.0;
+    scales[a] = s;
+    unscale[a] = 1.0 / (sA[0] * s);
+}
+
+__device__ __forceinline__ void split2(double x, __half& hi, __half& lo)
+{
+    const float xf = (float)x;                         // |x| <= 2^14: conversion error 2^-24 relative, below the lo plane
+    hi = __float2half_rn(xf);
+    const double rem = x - (double)__half2float(hi);
+    lo = __float2half_rn((float)(rem * (double)LO_SCALE));
+}
+
+// F (k x len, column-major fp64) -> planes [NP][ld] (row a contiguous along i), rows >= k zero
+__global__ void __launch_bounds__(256)
+k_split_factor(const double* __restrict__ F, int k, int64_t len, int64_t ld, int np, const double* __restrict__ scales,
+               __half* __restrict__ hi, __half* __restrict__ lo)
+{
+    extern __shared__ double tile[];                   // [64][k + 1]
+    const int64_t i0 = (int64_t)blockIdx.x * 64;
+    const int cnt = (int)min((int64_t)64, len - i0);
+    const int kp = k + 1;
+    for (int e = threadIdx.x; e < cnt * k; e += 256) tile[(e / k) * kp + (e % k)] = F[(int64_t)k * i0 + e];
+    __syncthreads();
+    for (int e = threadIdx.x; e < np * 64; e += 256) {
+        const int a = e / 64, ii = e % 64;
+        if (i0 + ii >= ld) continue;
+        __half h = __float2half_rn(0.f), l = h;
+        if (a < k && ii < cnt) split2(tile[ii * kp + a] * scales[a], h, l);
+        hi[(int64_t)a * ld + i0 + ii] = h;
+        lo[(int64_t)a * ld + i0 + ii] = l;
+    }
+}
+
+// max |A| over finite entries -> bit pattern (one atomicMax per block)
+__global__ void k_absmax(const double* __restrict__ A, int64_t total, unsigned long long* __restrict__ out)
+{
+    __shared__ unsigned long long red[32];
+    unsigned long long m = 0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const double v = fabs(A[e]);
+        if (!is_missing(v)) m = max(m, (unsigned long long)__double_as_longlong(v));
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = max(m, red[w]);
+        if (m) atomicMax(out, m);
+    }
+}
+
+// centred values are bounded by 2 max|A|
+__global__ void k_scale_from_max(const unsigned long long* __restrict__ mx, double* __restrict__ sA)
+{
+    sA[0] = pow2_scale(2.0 * __longlong_as_double((long long)mx[0]));
+}
+
+// mean over the finite entries of every column (warp per column) and of every row (thread per row)
+__global__ void k_col_means(const double* __restrict__ A, int64_t len, int64_t ncol, double* __restrict__ mean)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t j = warp; j < ncol; j += nwarp) {
+        double s = 0.0, c = 0.0;
+        for (int64_t i = lane; i < len; i += 32) {
+            const double a = A[i + len * j];
+            if (!is_missing(a)) { s += a; c += 1.0; }
+        }
+        s = warp_sum(s); c = warp_sum(c);
+        if (lane == 0) mean[j] = c > 0 ? s / c : 0.0;
+    }
+}
+
+__global__ void k_row_means(const double* __restrict__ A, int64_t len, int64_t ncol, double* __restrict__ mean)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    double s = 0.0, c = 0.0;
+    for (int64_t j = 0; j < ncol; j++) {
+        const double a = A[i + len * j];
+        if (!is_missing(a)) { s += a; c += 1.0; }
+    }
+    mean[i] = c > 0 ? s / c : 0.0;
+}
+
+// A (len x ncol, column-major fp64) -> planes of A - colmean (pitch ld_a, row j) and of A' - rowmean (pitch ld_t, row i);
+// non-finite entries become 0 in the planes (= the mean)
+__global__ void __launch_bounds__(256)
+k_split_matrix(const double* __restrict__ A, int64_t len, int64_t ncol, const double* __restrict__ sA,
+               const double* __restrict__ colmean, const double* __restrict__ rowmean,
+               __half* __restrict__ a_hi, __half* __restrict__ a_lo, int64_t ld_a,
+               __half* __restrict__ t_hi, __half* __restrict__ t_lo, int64_t ld_t)
+{
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 8
+    const int64_t i0 = (int64_t)blockIdx.x * 32, j0 = (int64_t)blockIdx.y * 32;
+    const double s = sA[0];
+    const double nanv = __longlong_as_double(0x7ff8000000000000ll);
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t i = i0 + tx, j = j0 + r;
+        double a = nanv;
+        if (i < len && j < ncol) {
+            a = A[i + len * j];
+            __half h = __float2half_rn(0.f), l = h;
+            if (!is_missing(a)) split2((a - colmean[j]) * s, h, l);
+            a_hi[i + ld_a * j] = h;
+            a_lo[i + ld_a * j] = l;
+        }
+        tile[r][tx] = a;
+    }
+    __syncthreads();
+    if (t_hi) {
+#pragma unroll
+        for (int r = ty; r < 32; r += 8) {
+            const int64_t j = j0 + tx, i = i0 + r;
+            if (i < len && j < ncol) {
+                const double a = tile[tx][r];
+                __half h = __float2half_rn(0.f), l = h;
+                if (!is_missing(a)) split2((a - rowmean[i]) * s, h, l);
+                t_hi[j + ld_t * i] = h; t_lo[j + ld_t * i] = l;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- host side
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn encode_fn()
+{
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        NNLM_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        if (!p || qres != cudaDriverEntryPointSuccess) throw Error(NNLM_E_CUDA, "cuTensorMapEncodeTiled is not available");
+        fn = reinterpret_cast<EncodeFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp16 tensor: inner extent `inner` (contiguous), `rows` rows of pitch ld elements; box = 64 x box_rows, SWIZZLE_128B
+CUtensorMap make_map(const __half* base, int64_t inner, int64_t rows, int64_t ld, int box_rows)
+{
+    CUtensorMap m;
+    const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(__half)};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult rc = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) throw Error(NNLM_E_CUDA, "cuTensorMapEncodeTiled failed (rc " + std::to_string((int)rc) + ")");
+    return m;
+}
+
+int sm_count()
+{
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int NP, int STAGES>
+void launch_np(const CrossPlan& plan, const __half* a_hi, const __half* a_lo, const __half* f_hi, const __half* f_lo,
+               const double* unscale, const double* center, const double* fsum, double* Qp, cudaStream_t st)
+{
+    constexpr size_t smem = (size_t)STAGES * (2 * BM * BK * 2 + 2 * NP * BK * 2) + 1024 /*alignment slack*/ + 256;
+    auto kern = k_cross_tc<NP, STAGES>;
+    NNLM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const CUtensorMap mA_hi = make_map(a_hi, plan.len, plan.ncol, plan.ld_a, BM);
+    const CUtensorMap mA_lo = make_map(a_lo, plan.len, plan.ncol, plan.ld_a, BM);
+    const CUtensorMap mF_hi = make_map(f_hi, plan.len, NP, plan.ld_f, NP);
+    const CUtensorMap mF_lo = make_map(f_lo, plan.len, NP, plan.ld_f, NP);
+    CrossParams p;
+    p.ncol = plan.ncol; p.kblocks = plan.kblocks; p.units = plan.units; p.k = plan.k; p.Qp = Qp; p.unscale = unscale;
+    static const int drain_env = [] { const char* e = getenv("NNLM_TC_DRAIN"); const int v = e ? atoi(e) : 0; return v > 0 ? v : DRAIN_DEFAULT; }();
+    p.drain = drain_env;
+    p.center = center; p.fsum = fsum;
+    NNLM_CUDA_CHECK(cudaMemsetAsync(Qp, 0, sizeof(double) * (size_t)plan.slots * plan.ncol * plan.k, st));
+    kern<<<plan.grid, THREADS, smem, st>>>(mA_hi, mA_lo, mF_hi, mF_lo, p);
+    NNLM_LAUNCHED();
+}
+
+}  // namespace
+
+bool cross_tc_supported(int k) { return k >= 1 && k <= 64; }
+int cross_tc_np(int k) { return k <= 32 ? 32 : 64; }
+int64_t cross_tc_ld(int64_t len) { return (len + 7) / 8 * 8; }     // TMA row pitch must be a multiple of 16 bytes
+
+CrossPlan cross_tc_plan(int k, int64_t len, int64_t ncol)
+{
+    CrossPlan pl;
+    pl.k = k; pl.len = len; pl.ncol = ncol;
+    pl.np = cross_tc_np(k);
+    pl.ld_a = cross_tc_ld(len);
+    pl.ld_f = cross_tc_ld(len);
+    pl.tiles = ceil_div(ncol, BM);
+    pl.kblocks = ceil_div(len, BK);
+    pl.units = pl.tiles * pl.kblocks;
+    pl.grid = (int)std::min<int64_t>(sm_count(), pl.units);
+    // most CTAs that touch one tile
+    int64_t worst = 1;
+    for (int64_t t = 0; t < pl.tiles; t++) {
+        const int64_t first = first_cta_of_unit(t * pl.kblocks, pl.units, pl.grid);
+        const int64_t last = first_cta_of_unit((t + 1) * pl.kblocks - 1, pl.units, pl.grid);
+        worst = std::max(worst, last - first + 1);
+    }
+    pl.slots = (int)worst;
+    return pl;
+}
+
+void launch_cross_tc(const CrossPlan& plan, const __half* a_hi, const __half* a_lo, const __half* f_hi, const __half* f_lo,
+                     const double* unscale, const double* center, const double* fsum, double* Qp, cudaStream_t st)
+{
+    NNLM_REQUIRE(cross_tc_supported(plan.k), "tensor-core cross-product supports rank k <= 64");
+    if (plan.np == 32) launch_np<32, 5>(plan, a_hi, a_lo, f_hi, f_lo, unscale, center, fsum, Qp, st);
+    else               launch_np<64, 4>(plan, a_hi, a_lo, f_hi, f_lo, unscale, center, fsum, Qp, st);
+}
+
+void launch_means(const double* A, int64_t len, int64_t ncol, double* colmean, double* rowmean, cudaStream_t st)
+{
+    k_col_means<<<(int)std::min<int64_t>(ceil_div(ncol * 32, 256), 148 * 8), 256, 0, st>>>(A, len, ncol, colmean);
+    NNLM_LAUNCHED();
+    if (rowmean) {
+        k_row_means<<<(unsigned)ceil_div(len, 128), 128, 0, st>>>(A, len, ncol, rowmean);
+        NNLM_LAUNCHED();
+    }
+}
+
+void launch_absmax_scale(const double* A, int64_t total, unsigned long long* scratch, double* sA, cudaStream_t st)
+{
+    NNLM_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(unsigned long long), st));
+    k_absmax<<<(int)std::min<int64_t>(ceil_div(total, 1024), 148 * 8), 1024, 0, st>>>(A, total, scratch);
+    NNLM_LAUNCHED();
+    k_scale_from_max<<<1, 1, 0, st>>>(scratch, sA);
+    NNLM_LAUNCHED();
+}
+
+void launch_split_matrix(const double* A, int64_t len, int64_t ncol, const double* sA, const double* colmean,
+                         const double* rowmean, __half* a_hi, __half* a_lo, int64_t ld_a,
+                         __half* t_hi, __half* t_lo, int64_t ld_t, cudaStream_t st)
+{
+    NNLM_REQUIRE(ceil_div(ncol, 32) <= 65535, "too many columns for the plane conversion grid");
+    dim3 grid((unsigned)ceil_div(len, 32), (unsigned)ceil_div(ncol, 32));
+    k_split_matrix<<<grid, 256, 0, st>>>(A, len, ncol, sA, colmean, rowmean, a_hi, a_lo, ld_a, t_hi, t_lo, ld_t);
+    NNLM_LAUNCHED();
+}
+
+void launch_split_factor(const double* F, int k, int64_t len, int64_t ld, int np, const double* sA, unsigned long long* rowmax,
+                         double* scales, double* unscale, __half* hi, __half* lo, cudaStream_t st)
+{
+    NNLM_CUDA_CHECK(cudaMemsetAsync(rowmax, 0, sizeof(unsigned long long) * np, st));
+    const int64_t total = (int64_t)k * len;
+    k_rowmax<<<(int)std::min<int64_t>(ceil_div(total, 256 * 8), 148 * 4), 256, sizeof(unsigned long long) * k, st>>>(F, k, len, rowmax);
+    NNLM_LAUNCHED();
+    k_make_scales<<<1, 128, 0, st>>>(rowmax, k, np, sA, scales, unscale);
+    NNLM_LAUNCHED();
+    k_split_factor<<<(unsigned)ceil_div(ld, 64), 256, sizeof(double) * 64 * (k + 1), st>>>(F, k, len, ld, np, scales, hi, lo);
+    NNLM_LAUNCHED();
+}
+
+}  // namespace nnlm

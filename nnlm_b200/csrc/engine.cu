@@ -64,7 +64,8 @@ Engine::Engine(int64_t n, int64_t m, int k, int method, int precision, int devic
     if (device_ < 0) NNLM_CUDA_CHECK(cudaGetDevice(&device_));
     NNLM_CUDA_CHECK(cudaSetDevice(device_));
     // precision policy (include/nnlm_b200.h): the resident copies of A are fp64 unless the fast path is requested
-    storage_ = (precision == NNLM_PREC_FAST) ? Storage::F32 : Storage::F64;
+    precision_req_ = precision;
+    storage_ = (precision == NNLM_PREC_FAST) ? Storage::F32 : Storage::F64;       // refined in ingest_device_A
     NNLM_CUDA_CHECK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
     Wt_.alloc((size_t)k_ * n_);
     H_.alloc((size_t)k_ * m_);
@@ -86,6 +87,14 @@ void Engine::ensure_scratch()
     if (method_ <= 2) {
         size_t q = (size_t)cross_simt_splits(k_, n_, m_) * k_ * m_;
         if (both_sides_) q = std::max(q, (size_t)cross_simt_splits(k_, m_, n_) * k_ * n_);
+        if (cross_tc_supported(k_)) {
+            plan_h_ = cross_tc_plan(k_, n_, m_);
+            q = std::max(q, (size_t)plan_h_.slots * k_ * m_);
+            if (both_sides_) {
+                plan_w_ = cross_tc_plan(k_, m_, n_);
+                q = std::max(q, (size_t)plan_w_.slots * k_ * n_);
+            }
+        }
         Qp_.alloc(q);
     } else {
         Yr_.alloc((size_t)k_ * big);
@@ -123,20 +132,52 @@ void Engine::ingest_device_A(const double* dA)
         NNLM_CUDA_CHECK(cudaMemcpyAsync(A64_.p, dA, cnt * sizeof(double), cudaMemcpyDeviceToDevice, st_));
     }
     const int64_t parts = ingest_part_count(n_, m_);
-    if (storage_ == Storage::F64) {
-        if (both_sides_) At64_.alloc(cnt);
-        launch_ingest<double>(A64_.p, n_, m_, 0, m_, nullptr, both_sides_ ? At64_.p : nullptr, red_part_.p, st_);
-    } else {
-        A32_.alloc(cnt);
-        if (both_sides_) At32_.alloc(cnt);
-        launch_ingest<float>(A64_.p, n_, m_, 0, m_, A32_.p, both_sides_ ? At32_.p : nullptr, red_part_.p, st_);
-    }
+    // pass 1: missing-entry count and the constant part of the KL distance (src/nnmf.cpp:64-73)
+    launch_ingest<double>(A64_.p, n_, m_, 0, m_, nullptr, nullptr, red_part_.p, st_);
     launch_reduce_partials(red_part_.p, parts, 2, small_.p, st_);
     NNLM_CUDA_CHECK(cudaMemcpyAsync(host_small_.p, small_.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st_));
     sync();
     d2h_bytes += 2 * sizeof(double);
     kl_const_sum_ = host_small_.p[0];
     n_missing_ = (int64_t)host_small_.p[1];
+    // pass 2: the resident copies, in the storage the precision policy selects (include/nnlm_b200.h)
+    if (precision_req_ == NNLM_PREC_FAST && method_ <= 2 && cross_tc_supported(k_) && !use_missing_path())
+        storage_ = Storage::F16X2;
+    if (storage_ == Storage::F64) {
+        if (both_sides_) {
+            At64_.alloc(cnt);
+            launch_ingest<double>(A64_.p, n_, m_, 0, m_, nullptr, At64_.p, red_part_.p, st_);
+        }
+    } else if (storage_ == Storage::F32) {
+        A32_.alloc(cnt);
+        if (both_sides_) At32_.alloc(cnt);
+        launch_ingest<float>(A64_.p, n_, m_, 0, m_, A32_.p, both_sides_ ? At32_.p : nullptr, red_part_.p, st_);
+    } else {
+        const int64_t ld_n = cross_tc_ld(n_), ld_m = cross_tc_ld(m_);
+        const int np = cross_tc_np(k_);
+        a_hi_.alloc((size_t)ld_n * m_); a_lo_.alloc((size_t)ld_n * m_);
+        if (both_sides_) { t_hi_.alloc((size_t)ld_m * n_); t_lo_.alloc((size_t)ld_m * n_); }
+        const int64_t ld_f = std::max(ld_n, both_sides_ ? ld_m : (int64_t)0);
+        f_hi_.alloc((size_t)np * ld_f); f_lo_.alloc((size_t)np * ld_f);
+        scale_a_.alloc(1); fscales_.alloc(np); unscale_.alloc(np); rowmax_.alloc(np + 1);
+        // pitch padding of the planes must read as zero (it is never written by the conversion kernels)
+        NNLM_CUDA_CHECK(cudaMemsetAsync(a_hi_.p, 0, a_hi_.bytes(), st_));
+        NNLM_CUDA_CHECK(cudaMemsetAsync(a_lo_.p, 0, a_lo_.bytes(), st_));
+        if (both_sides_) {
+            NNLM_CUDA_CHECK(cudaMemsetAsync(t_hi_.p, 0, t_hi_.bytes(), st_));
+            NNLM_CUDA_CHECK(cudaMemsetAsync(t_lo_.p, 0, t_lo_.bytes(), st_));
+        }
+        colmean_.alloc(m_);
+        if (both_sides_) rowmean_.alloc(n_);
+        launch_means(A64_.p, n_, m_, colmean_.p, both_sides_ ? rowmean_.p : nullptr, st_);
+        launch_absmax_scale(A64_.p, (int64_t)cnt, rowmax_.p + np, scale_a_.p, st_);
+        launch_split_matrix(A64_.p, n_, m_, scale_a_.p, colmean_.p, both_sides_ ? rowmean_.p : nullptr, a_hi_.p, a_lo_.p, ld_n,
+                            both_sides_ ? t_hi_.p : nullptr, both_sides_ ? t_lo_.p : nullptr, ld_m, st_);
+        // the error evaluation (trace iterations only) reads an fp32 copy of A
+        A32_.alloc(cnt);
+        launch_ingest<float>(A64_.p, n_, m_, 0, m_, A32_.p, nullptr, red_part_.p, st_);
+    }
+    sync();
     if (storage_ != Storage::F64) A64_.release();
 }
 
@@ -217,18 +258,17 @@ void Engine::run_half_t(const Half& h)
         timer.begin(KernelTimer::CROSS, st_);
         launch_cross_simt<TA>(h.Y, A, k_, h.len, h.ncol, splits, Qp_.p, st_);
         timer.end(st_);
-        timer.begin(KernelTimer::GRAM, st_);
-        if (!missing) launch_gram(h.Y, k_, h.len, h.pen, gram_part_.p, G_.p, st_);        // update_with_missing.cpp:19-24
-        else launch_gram(h.Y, k_, h.len, nullptr, gram_part_.p, Graw_.p, st_);
-        timer.end(st_);
-        timer.begin(KernelTimer::SOLVE, st_);
-        if (!missing)
-            launch_solve_ls(method_, h.X, G_.p, Qp_.p, splits, h.mask, k_, h.ncol, h.pen[2], inner_max_iter_,
-                            inner_rel_tol_, sweeps_.p, st_);
-        else
+        if (!missing) {
+            solve_dense_ls(h, splits);
+        } else {
+            timer.begin(KernelTimer::GRAM, st_);
+            launch_gram(h.Y, k_, h.len, nullptr, gram_part_.p, Graw_.p, st_);
+            timer.end(st_);
+            timer.begin(KernelTimer::SOLVE, st_);
             launch_solve_ls_missing<TA>(method_, h.X, h.Y, A, Graw_.p, Qp_.p, splits, h.mask, k_, h.len, h.ncol, h.pen,
                                         inner_max_iter_, inner_rel_tol_, sweeps_.p, st_);
-        timer.end(st_);
+            timer.end(st_);
+        }
     } else {
         timer.begin(KernelTimer::GRAM, st_);
         launch_rowsum(h.Y, k_, h.len, gram_part_.p, sumY_.p, st_);                         // :27
@@ -239,6 +279,34 @@ void Engine::run_half_t(const Half& h)
                             inner_rel_tol_, missing ? 1 : 0, wh_.p, sweeps_.p, st_);
         timer.end(st_);
     }
+}
+
+void Engine::solve_dense_ls(const Half& h, int splits)
+{
+    timer.begin(KernelTimer::GRAM, st_);
+    launch_gram(h.Y, k_, h.len, h.pen, gram_part_.p, G_.p, st_);                          // update_with_missing.cpp:19-24
+    timer.end(st_);
+    timer.begin(KernelTimer::SOLVE, st_);
+    if (method_ == 1 && scd_tpc_supported(k_))
+        launch_scd_tpc(h.X, G_.p, Qp_.p, splits, h.mask, k_, h.ncol, h.pen[2], inner_max_iter_, inner_rel_tol_, sweeps_.p, st_);
+    else
+        launch_solve_ls(method_, h.X, G_.p, Qp_.p, splits, h.mask, k_, h.ncol, h.pen[2], inner_max_iter_, inner_rel_tol_,
+                        sweeps_.p, st_);
+    timer.end(st_);
+}
+
+void Engine::run_half_tc(const Half& h, bool w_side)
+{
+    const CrossPlan& plan = w_side ? plan_w_ : plan_h_;
+    timer.begin(KernelTimer::GRAM, st_);
+    launch_split_factor(h.Y, k_, h.len, plan.ld_f, plan.np, scale_a_.p, rowmax_.p, fscales_.p, unscale_.p, f_hi_.p, f_lo_.p, st_);
+    launch_rowsum(h.Y, k_, h.len, gram_part_.p, sumY_.p, st_);
+    timer.end(st_);
+    timer.begin(KernelTimer::CROSS, st_);
+    launch_cross_tc(plan, w_side ? t_hi_.p : a_hi_.p, w_side ? t_lo_.p : a_lo_.p, f_hi_.p, f_lo_.p, unscale_.p,
+                    w_side ? rowmean_.p : colmean_.p, sumY_.p, Qp_.p, st_);
+    timer.end(st_);
+    solve_dense_ls(h, plan.slots);
 }
 
 void Engine::run_half(const Half& h)
@@ -252,13 +320,43 @@ void Engine::half_w()
 {
     NNLM_REQUIRE(both_sides_, "this engine was created for the H-half only");
     const void* At = storage_ == Storage::F64 ? (const void*)At64_.p : (const void*)At32_.p;
-    run_half(Half{Wt_.p, n_, H_.p, m_, At, has_wm_ ? Wm_.p : nullptr, alpha_});
+    const Half h{Wt_.p, n_, H_.p, m_, At, has_wm_ ? Wm_.p : nullptr, alpha_};
+    if (storage_ == Storage::F16X2) { DeviceGuard g(device_); run_half_tc(h, true); }
+    else run_half(h);
 }
 
 void Engine::half_h()
 {
     const void* A = storage_ == Storage::F64 ? (const void*)A64_.p : (const void*)A32_.p;
-    run_half(Half{H_.p, m_, Wt_.p, n_, A, has_hm_ ? Hm_.p : nullptr, beta_});
+    const Half h{H_.p, m_, Wt_.p, n_, A, has_hm_ ? Hm_.p : nullptr, beta_};
+    if (storage_ == Storage::F16X2) { DeviceGuard g(device_); run_half_tc(h, false); }
+    else run_half(h);
+}
+
+void Engine::cross_only(double* Q_host)
+{
+    DeviceGuard g(device_);
+    int splits;
+    if (storage_ == Storage::F16X2) {
+        launch_split_factor(Wt_.p, k_, n_, plan_h_.ld_f, plan_h_.np, scale_a_.p, rowmax_.p, fscales_.p, unscale_.p, f_hi_.p, f_lo_.p, st_);
+        launch_rowsum(Wt_.p, k_, n_, gram_part_.p, sumY_.p, st_);
+        launch_cross_tc(plan_h_, a_hi_.p, a_lo_.p, f_hi_.p, f_lo_.p, unscale_.p, colmean_.p, sumY_.p, Qp_.p, st_);
+        splits = plan_h_.slots;
+    } else {
+        splits = cross_simt_splits(k_, n_, m_);
+        if (storage_ == Storage::F64) launch_cross_simt<double>(Wt_.p, A64_.p, k_, n_, m_, splits, Qp_.p, st_);
+        else launch_cross_simt<float>(Wt_.p, A32_.p, k_, n_, m_, splits, Qp_.p, st_);
+    }
+    const size_t per = (size_t)k_ * m_;
+    std::vector<double> tmp(per * splits);
+    NNLM_CUDA_CHECK(cudaMemcpyAsync(tmp.data(), Qp_.p, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    sync();
+    d2h_bytes += tmp.size() * sizeof(double);
+    for (size_t e = 0; e < per; e++) {
+        double s = 0;
+        for (int sp = 0; sp < splits; sp++) s += tmp[(size_t)sp * per + e];
+        Q_host[e] = s;
+    }
 }
 
 void Engine::errors(ErrorTerms* out)

@@ -75,6 +75,8 @@ public:
     void half_h();      // solve for H given W
     // generic single half-iteration on explicit operands already on the device (nnlm_update / nnlm_nnlm)
     void errors(ErrorTerms* out);                 // synchronises the stream
+    // diagnostic: Q = Wt * A (k x m, missing entries of A read as zero) through the cross-product path of the current storage
+    void cross_only(double* Q_host);
     uint64_t take_sweeps();                       // read and reset total_raw_iter (synchronises)
     void sync();
 
@@ -104,6 +106,8 @@ private:
     };
     void run_half(const Half& h);
     template <typename TA> void run_half_t(const Half& h);
+    void run_half_tc(const Half& h, bool w_side);
+    void solve_dense_ls(const Half& h, int splits);
     void ensure_scratch();
 
     int64_t n_, m_;
@@ -118,6 +122,12 @@ private:
 
     DevBuf<double> A64_, At64_;     // n x m and m x n, column-major
     DevBuf<float> A32_, At32_;
+    // fp16 hi/lo planes for the tensor-core cross-product (cross_tc.cu): A as [m][ld(n)], A' as [n][ld(m)], factor [np][ld]
+    DevBuf<__half> a_hi_, a_lo_, t_hi_, t_lo_, f_hi_, f_lo_;
+    DevBuf<double> scale_a_, fscales_, unscale_, colmean_, rowmean_;
+    DevBuf<unsigned long long> rowmax_;
+    CrossPlan plan_h_, plan_w_;
+    int precision_req_ = NNLM_PREC_AUTO;
     DevBuf<double> Wt_, H_;         // k x n, k x m
     DevBuf<uint8_t> Wm_, Hm_;       // k x n, k x m or empty
     bool has_wm_ = false, has_hm_ = false;

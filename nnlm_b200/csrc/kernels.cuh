@@ -4,6 +4,8 @@
 // Both halves of an iteration use the same launchers with the roles swapped (src/nnmf.cpp:117-119,131-133):
 //   H-half: (H, W,  A   : len = n, ncol = m)      W-half: (W, H, A^T : len = m, ncol = n).
 #pragma once
+#include <cuda_fp16.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -52,12 +54,44 @@ int  cross_simt_splits(int k, int64_t len, int64_t ncol);
 template <typename TA>
 void launch_cross_simt(const double* Y, const TA* A, int k, int64_t len, int64_t ncol, int splits, double* Qp, cudaStream_t st);
 
+// ---- cross_tc.cu: K2 on tcgen05 (fp16 hi/lo planes, fp32 TMEM accumulate drained into fp64, stream-K) ----
+struct CrossPlan {
+    int k = 0, np = 0, grid = 0, slots = 0;
+    int64_t len = 0, ncol = 0, ld_a = 0, ld_f = 0, tiles = 0, kblocks = 0, units = 0;
+};
+bool      cross_tc_supported(int k);
+int       cross_tc_np(int k);                 // padded rank (rows of the factor planes)
+int64_t   cross_tc_ld(int64_t len);           // row pitch (elements) of a plane whose rows hold `len` contraction indices
+CrossPlan cross_tc_plan(int k, int64_t len, int64_t ncol);
+// Qp[slot][ncol][k] (slots = plan.slots, zero-filled here) = partial cross-products; sum over slots = F * A.
+// a_* : planes of the A copy of this half (row j = column j of the matrix, pitch plan.ld_a); f_* : planes of the factor.
+// center[ncol] = the per-column mean that was subtracted from A before the split, fsum[k] = rowSums(F): the mean component
+// center[j]*fsum[a] is added back in fp64 (slot 0).
+void launch_cross_tc(const CrossPlan& plan, const __half* a_hi, const __half* a_lo, const __half* f_hi, const __half* f_lo,
+                     const double* unscale, const double* center, const double* fsum, double* Qp, cudaStream_t st);
+// means over the finite entries of the columns (ncol values) and rows (len values, nullptr to skip) of A
+void launch_means(const double* A, int64_t len, int64_t ncol, double* colmean, double* rowmean, cudaStream_t st);
+// sA[0] = power-of-two scale of A from max |A| (scratch: one u64)
+void launch_absmax_scale(const double* A, int64_t total, unsigned long long* scratch, double* sA, cudaStream_t st);
+// A (len x ncol col-major fp64) -> planes of A (pitch ld_a) and of A' (pitch ld_t; pass nullptr to skip)
+void launch_split_matrix(const double* A, int64_t len, int64_t ncol, const double* sA, const double* colmean,
+                         const double* rowmean, __half* a_hi, __half* a_lo, int64_t ld_a,
+                         __half* t_hi, __half* t_lo, int64_t ld_t, cudaStream_t st);
+// F (k x len col-major fp64) -> planes [np][ld] with per-row power-of-two scales; unscale[a] = 1/(sA*scale[a])
+void launch_split_factor(const double* F, int k, int64_t len, int64_t ld, int np, const double* sA, unsigned long long* rowmax,
+                         double* scales, double* unscale, __half* hi, __half* lo, cudaStream_t st);
+
 // ---- solve_ls.cu: K3/K4/K5 — warp-per-column sequential coordinate descent / Lee multiplicative, square loss ----
 // X (k x ncol) in/out; G regularised Gram (k x k); Qp split-K partials of Wt*A (splits x k x ncol); mask k x ncol bytes or null;
 // l1 = beta(2); sweeps: device counter incremented by the summed sweep count (total_raw_iter).
 void launch_solve_ls(int method, double* X, const double* G, const double* Qp, int splits, const uint8_t* mask,
                      int k, int64_t ncol, double l1, unsigned max_iter, double rel_tol, unsigned long long* sweeps,
                      cudaStream_t st);
+
+// ---- solve_scd_tpc.cu: K3/K4 thread-per-column SCD (method 1, dense A, k <= 64): same contract as launch_solve_ls ----
+bool scd_tpc_supported(int k);
+void launch_scd_tpc(double* X, const double* G, const double* Qp, int splits, const uint8_t* mask, int k, int64_t ncol,
+                    double l1, unsigned max_iter, double rel_tol, unsigned long long* sweeps, cudaStream_t st);
 
 // ---- solve_ls_missing.cu: K9 + K4/K5, the NA path of the square loss (src/update_with_missing.cpp:58-117) ----
 // Y k x len (the fixed factor), A len x ncol (non-finite = missing), Gfull the raw (unregularised) Gram of Y,
