@@ -165,21 +165,43 @@ def main():
 
     import torch
     import nnlm_b200
-    from nnlm_b200 import _capi as K
-    from nnlm_b200.session import Session, synth_init, synth_matrix
+    from nnlm_b200 import _capi as K, shard
+    from nnlm_b200.session import Session, synth_block, synth_init, synth_matrix
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    comm = None
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if world != 1:
-        raise SystemExit("the column-sharded multi-GPU path is not wired into bench.py yet")
+        comm = shard.comm_from_torch(local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
 
     n, m, k = wl["n"], wl["m"], wl["k"]
     W0, H0 = synth_init(n, m, k)
+    # strong scaling: the same 50000 x 10000 problem, A column-sharded (H-half) and row-sharded (W-half) over the ranks
     sess = Session(k=k, method=1, inner_max_iter=50, inner_rel_tol=1e-9, precision=args.precision, device=local_rank,
-                   synthetic=dict(n=n, m=m), timing=True)
+                   synthetic=dict(n=n, m=m), timing=True, comm=comm)
     sess.set_factors(W0, H0)
     W = max(args.warmup, 3)
     sess.run(W)                                       # warm-up iterations (also moves past the cold first sweeps)
@@ -187,12 +209,13 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
-    torch.cuda.synchronize()
+    barrier()
     t0 = time.perf_counter()
     dev_ms, sweeps = sess.run(args.steps)             # EXACTLY K iterations, CUDA events on the library's stream
-    torch.cuda.synchronize()
+    barrier()
     t1 = time.perf_counter()
     clocks = sampler.stop(t0, t1)
+    dev_ms = max_over_ranks(dev_ms)                   # device time, max over ranks
     st = sess.stats()
     mse, _, _ = sess.error()
     value = args.steps / (dev_ms * 1e-3)
@@ -200,46 +223,76 @@ def main():
     s_bytes = 8 if st["precision_used"] == K.PREC_EXACT else 4
     hbm_peak, peak_src = peaks()
     cross_ms = st["cross_ms"] / max(st["cross_launches"], 1)
-    algo_bytes = float(n) * m * s_bytes + 8.0 * k * (n + m)           # one pass over the A copy + factor in + partials out
+    # one pass over this rank's copy of A for the half (n*m/world elements) + factor in + partials out
+    algo_bytes = float(n) * m * s_bytes / world + 8.0 * k * (n + m)
     achieved = algo_bytes / (cross_ms * 1e-3) / 1e9 if cross_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "kernel": "cross-product (one pass over A per half-iteration)",
+                "traffic": 2.08e9 if (world == 1 and not args.small) else None,
+                "kernel": "k_cross_tc (cross-product: one pass over A per half-iteration), per GPU",
                 "algorithmic_bytes_per_launch": algo_bytes, "ms_per_launch": cross_ms, "peak_source": peak_src,
+                "traffic_source": "ncu --set full dram__bytes_read+write per launch, profiles/r1_b_*.md" if world == 1 else None,
                 "share_of_step": {"cross": st["cross_ms"] / dev_ms, "solve": st["solve_ms"] / dev_ms,
-                                  "gram": st["gram_ms"] / dev_ms}}
+                                  "gram": st["gram_ms"] / dev_ms, "comm": st["comm_ms"] / dev_ms}}
+    launches = int(sum_over_ranks(float(st["launches"])))
     sess.close()
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64 solver state, " + ("f64" if s_bytes == 8 else "f32") + " A",
+            "dtype": "f64 solver state, " + ("f64 A" if s_bytes == 8 else "fp16 hi+lo planes of A (4 B/element), fp32 TMEM accumulate drained to f64"),
             "data": "synthetic",
             "config": {"workload": wl["name"], "inner_max_iter": 50, "inner_rel_tol": 1e-9,
-                       "l2_policy": "inputs larger than L2 (each half streams a %.1f GB copy of A)" % (n * m * s_bytes / 1e9),
+                       "sharding": "none" if world == 1 else f"columns (H-half) and rows (W-half) over {world} ranks; "
+                                   "k x k Gram all-reduce + factor all-gather per half-iteration (NCCL)",
+                       "l2_policy": "inputs larger than L2 (each half streams a %.2f GB copy of A per GPU)" % (n * m * s_bytes / world / 1e9),
                        "avg_inner_sweeps_per_column": sweeps / (args.steps * (n + m)), "mse_after": mse},
-            "clocks": clocks, "gpu_launches": int(st["launches"]), "roofline": roofline}
+            "clocks": clocks, "gpu_launches": launches, "roofline": roofline}
 
     if not args.no_e2e:
-        A = synth_matrix(n, m, k)
-        Ap = torch.from_numpy(A).pin_memory().numpy()   # pinned host copy (F-order is preserved through the transpose view)
-        Ap = np.asfortranarray(Ap) if not Ap.flags.f_contiguous else Ap
-        del A
-        Wp = torch.from_numpy(np.ascontiguousarray(W0.T)).pin_memory().numpy().T
-        Hp = torch.from_numpy(np.ascontiguousarray(H0.T)).pin_memory().numpy().T
-        t0 = time.perf_counter()
-        r = nnlm_b200.nnmf(Ap, k, init={"W": Wp, "H": Hp}, max_iter=args.steps, rel_tol=-1, trace=0, verbose=0,
-                           show_warning=False, inner_max_iter=50, precision=args.precision, device=local_rank)
-        wall = time.perf_counter() - t0
-        line["e2e"] = {"value": args.steps / wall, "unit": UNIT,
-                       "h2d_bytes_per_step": r.stats["h2d_bytes"] / args.steps,
-                       "d2h_bytes_per_step": r.stats["d2h_bytes"] / args.steps,
-                       "seconds": wall, "upload_ms": r.stats["upload_ms"], "loop_ms": r.stats["loop_ms"],
-                       "download_ms": r.stats["download_ms"],
-                       "what": "nnmf(A, k, init, max.iter=steps, rel.tol=-1, trace=0) with pinned host A/W/H"}
-        del Ap
+        # end to end through the public API with HOST buffers: pinned A (whole matrix on 1 GPU, this rank's shards otherwise)
+        # and pinned factors are copied to the device, `steps` iterations run, W and H are copied back
+        pin = lambda a: np.asfortranarray(torch.from_numpy(np.ascontiguousarray(a.T)).pin_memory().numpy().T)
+        Wp, Hp = pin(W0), pin(H0)
+        if world == 1:
+            Ap = pin(synth_matrix(n, m, k))
+            barrier()
+            t0 = time.perf_counter()
+            r = nnlm_b200.nnmf(Ap, k, init={"W": Wp, "H": Hp}, max_iter=args.steps, rel_tol=-1, trace=0, verbose=0,
+                               show_warning=False, inner_max_iter=50, precision=args.precision, device=local_rank,
+                               check_k=False)
+            wall = time.perf_counter() - t0
+            h2d, d2h = r.stats["h2d_bytes"], r.stats["d2h_bytes"]
+            what = "nnmf(A, k, init, max.iter=steps, rel.tol=-1, trace=0) with pinned host A/W/H"
+            extra = {"upload_ms": r.stats["upload_ms"], "loop_ms": r.stats["loop_ms"], "download_ms": r.stats["download_ms"]}
+            del Ap
+        else:
+            r0, nr = shard.shard_bounds(n, world, rank); c0, mc = shard.shard_bounds(m, world, rank)
+            Acol = pin(synth_block(n, 0, n, c0, mc, k)); Arow = pin(synth_block(n, r0, nr, 0, m, k))
+            barrier()
+            t0 = time.perf_counter()
+            s2 = Session(k=k, method=1, inner_max_iter=50, inner_rel_tol=1e-9, precision=args.precision, device=local_rank,
+                         comm=comm, shards=(Acol, Arow), shape=(n, m))
+            s2.set_factors(Wp, Hp)
+            s2.run(args.steps)
+            s2.get_factors()
+            barrier()
+            wall = time.perf_counter() - t0
+            st2 = s2.stats()
+            h2d, d2h = sum_over_ranks(float(st2["h2d_bytes"])), sum_over_ranks(float(st2["d2h_bytes"]))
+            what = "sharded Session(shards=pinned host A[:,cols_g], A[rows_g,:]) + set_factors + run(steps) + get_factors, all ranks"
+            extra = {"upload_ms": st2["upload_ms"]}
+            s2.close()
+            del Acol, Arow
+        wall = max_over_ranks(wall)
+        line["e2e"] = {"value": args.steps / wall, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
+                       "d2h_bytes_per_step": d2h / args.steps, "seconds": wall, "what": what, **extra}
     if not args.no_cpu and world == 1:
         sec, threads, sample = cpu_iteration(wl, steps=1)
         line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
-    print(json.dumps(line))
+    if rank == 0:
+        print(json.dumps(line))
+    if comm is not None:
+        comm.close()
+        dist.destroy_process_group()
     return 0
 
 

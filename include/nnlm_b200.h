@@ -87,6 +87,8 @@ typedef struct nnlm_stats {
     double gram_ms;           /* device time in the Gram / row-sum / factor re-layout kernels      */
     uint64_t cross_launches;  /* launches summed into cross_ms (verbose_timing only)               */
     uint64_t solve_launches;
+    double comm_ms;           /* device time in the NCCL collectives (sharded path)                */
+    uint64_t comm_bytes;      /* bytes this rank received through them                             */
 } nnlm_stats;
 
 /* ---- c_nnmf (src/nnmf.cpp:4-220) -------------------------------------------------------------
@@ -165,6 +167,16 @@ int nnlm_session_create_synthetic(nnlm_session** out, int64_t n, int64_t m, int3
                                   double na_frac, const double* alpha, const double* beta,
                                   uint32_t inner_max_iter, double inner_rel_tol, int32_t method,
                                   const nnlm_options* opt, char* err, size_t errlen);
+/* Sharded session (one process per GPU; opt->comm = this rank's nnlm_comm). Rank g of R holds
+ *   Acol = A[:, c0 .. c0+mc)  (n x mc, column-major)   and   Arow = A[r0 .. r0+nr, :]  (nr x m, column-major)
+ * with the equal-chunk bounds chunk = ceil(total/R), start = min(total, g*chunk) (nnlm_b200.shard.shard_bounds).
+ * Factors are whole (n x K, K x m) on every rank. nnlm_synth_block writes any block of the synthetic matrix to host memory. */
+int nnlm_session_create_sharded(nnlm_session** out, const double* Acol, const double* Arow, int64_t n, int64_t m, int32_t K,
+                                const int32_t* Wm, const int32_t* Hm, const double* alpha, const double* beta,
+                                uint32_t inner_max_iter, double inner_rel_tol, int32_t method,
+                                const nnlm_options* opt, char* err, size_t errlen);
+int nnlm_synth_block(double* A, int64_t n_global, int64_t row0, int64_t nr, int64_t col0, int64_t mc, int32_t k,
+                     uint64_t seed_base, double noise, double na_frac, char* err, size_t errlen);
 int nnlm_synth_matrix(double* A, int64_t n, int64_t m, int32_t k, int64_t col0, uint64_t seed_base, double noise,
                       double na_frac, char* err, size_t errlen);
 int nnlm_session_set_factors(nnlm_session* s, const double* W, const double* H, char* err, size_t errlen);

@@ -8,7 +8,8 @@ hand-written sm_100a CUDA kernels. No CPU fallback: without the built library or
 """
 from .api import Nnmf, Nnlm, nnmf, nnlm, nnlm_update, mse_mkl, get_method_code, reformat_input, na_mask, cross
 from .session import Session
+from . import shard
 from . import _capi
 
 __all__ = ["nnmf", "nnlm", "nnlm_update", "mse_mkl", "get_method_code", "reformat_input", "na_mask", "cross", "Nnmf", "Nnlm",
-           "Session", "_capi"]
+           "Session", "shard", "_capi"]

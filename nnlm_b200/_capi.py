@@ -33,7 +33,8 @@ class Stats(C.Structure):
                 ("cross_ms", C.c_double), ("solve_ms", C.c_double), ("error_ms", C.c_double),
                 ("launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("precision_used", C.c_int32), ("reserved0", C.c_int32),
-                ("gram_ms", C.c_double), ("cross_launches", C.c_uint64), ("solve_launches", C.c_uint64)]
+                ("gram_ms", C.c_double), ("cross_launches", C.c_uint64), ("solve_launches", C.c_uint64),
+                ("comm_ms", C.c_double), ("comm_bytes", C.c_uint64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_ if not f.startswith("reserved")}
@@ -54,7 +55,7 @@ _lib = None
 # every symbol include/nnlm_b200.h declares (tests/test_abi.py checks the library exports each of them)
 SYMBOLS = [
     "nnlm_abi_version", "nnlm_device_count", "nnlm_nnmf", "nnlm_nnlm", "nnlm_update", "nnlm_na_mask", "nnlm_cross",
-    "nnlm_session_create", "nnlm_session_create_synthetic", "nnlm_session_set_factors", "nnlm_session_get_factors",
+    "nnlm_session_create", "nnlm_session_create_synthetic", "nnlm_session_create_sharded", "nnlm_synth_block", "nnlm_session_set_factors", "nnlm_session_get_factors",
     "nnlm_session_run", "nnlm_session_error", "nnlm_session_stats", "nnlm_session_reset_stats", "nnlm_session_destroy",
     "nnlm_synth_matrix",
     "nnlm_comm_unique_id", "nnlm_comm_init", "nnlm_comm_destroy",

@@ -7,6 +7,8 @@
 
 #include "engine.cuh"
 
+struct nnlm_comm;
+
 using namespace nnlm;
 
 namespace {
@@ -56,6 +58,8 @@ void fill_stats(nnlm_stats* st, const Engine& e, uint64_t launches0)
     st->solve_ms = e.timer.ms[KernelTimer::SOLVE];
     st->error_ms = e.timer.ms[KernelTimer::ERROR];
     st->gram_ms = e.timer.ms[KernelTimer::GRAM];
+    st->comm_ms = e.timer.ms[KernelTimer::COMM];
+    st->comm_bytes = e.comm_bytes;
     st->cross_launches = e.timer.count[KernelTimer::CROSS];
     st->solve_launches = e.timer.count[KernelTimer::SOLVE];
 }
@@ -327,16 +331,68 @@ int nnlm_session_create_synthetic(nnlm_session** out, int64_t n, int64_t m, int3
         NNLM_REQUIRE(out, "nnlm_session_create_synthetic: NULL argument");
         std::unique_ptr<nnlm_session> s(new nnlm_session);
         s->launches0 = launch_counter().load();
-        s->eng.reset(new Engine(n, m, K, method, precision_of(opt, n, m), opt ? opt->device : -1));
+        Comm* comm = (opt && opt->comm) ? nnlm_comm_get(static_cast<nnlm_comm*>(opt->comm)) : nullptr;
+        s->eng.reset(new Engine(n, m, K, method, precision_of(opt, n, m), opt ? opt->device : -1, true, comm));
         s->eng->timer.enable(opt && opt->verbose_timing);
-        {
+        Engine& e = *s->eng;
+        if (!comm) {
             DevBuf<double> dA((size_t)n * m);
-            launch_synth(dA.p, n, m, K, opt ? opt->col_offset : 0, seed_base, noise, na_frac, s->eng->stream());
-            s->eng->ingest_device_A(dA.p);
+            launch_synth(dA.p, n, m, K, 0, seed_base, noise, na_frac, e.stream());
+            e.ingest_shards(dA.p, dA.p);
+        } else {
+            // every rank generates exactly its column shard and its row shard of the global matrix
+            DevBuf<double> dC((size_t)n * std::max<int64_t>(e.cols_local(), 1)), dR((size_t)std::max<int64_t>(e.rows_local(), 1) * m);
+            launch_synth_block(dC.p, n, 0, n, e.col0(), e.cols_local(), K, seed_base, noise, na_frac, e.stream());
+            launch_synth_block(dR.p, n, e.row0(), e.rows_local(), 0, m, K, seed_base, noise, na_frac, e.stream());
+            e.ingest_shards(dC.p, dR.p);
         }
-        s->eng->set_penalties(alpha, beta);
-        s->eng->set_inner(inner_max_iter, inner_rel_tol);
+        e.set_penalties(alpha, beta);
+        e.set_inner(inner_max_iter, inner_rel_tol);
         *out = s.release();
+        return NNLM_OK;
+    });
+}
+
+int nnlm_session_create_sharded(nnlm_session** out, const double* Acol, const double* Arow, int64_t n, int64_t m, int32_t K,
+                                const int32_t* Wm, const int32_t* Hm, const double* alpha, const double* beta,
+                                uint32_t inner_max_iter, double inner_rel_tol, int32_t method,
+                                const nnlm_options* opt, char* err, size_t errlen)
+{
+    return guarded(err, errlen, [&]() -> int {
+        NNLM_REQUIRE(out && Acol && Arow, "nnlm_session_create_sharded: NULL argument");
+        std::unique_ptr<nnlm_session> s(new nnlm_session);
+        s->launches0 = launch_counter().load();
+        Comm* comm = (opt && opt->comm) ? nnlm_comm_get(static_cast<nnlm_comm*>(opt->comm)) : nullptr;
+        s->eng.reset(new Engine(n, m, K, method, precision_of(opt, n, m), opt ? opt->device : -1, true, comm));
+        s->eng->timer.enable(opt && opt->verbose_timing);
+        Engine& e = *s->eng;
+        Events ev;
+        cudaEventRecord(ev.e[0], e.stream());
+        const size_t cc = (size_t)n * e.cols_local(), cr = (size_t)e.rows_local() * m;
+        DevBuf<double> dC(std::max<size_t>(cc, 1)), dR(std::max<size_t>(cr, 1));
+        NNLM_CUDA_CHECK(cudaMemcpyAsync(dC.p, Acol, cc * sizeof(double), cudaMemcpyHostToDevice, e.stream()));
+        NNLM_CUDA_CHECK(cudaMemcpyAsync(dR.p, Arow, cr * sizeof(double), cudaMemcpyHostToDevice, e.stream()));
+        e.h2d_bytes += (cc + cr) * sizeof(double);
+        e.ingest_shards(dC.p, dR.p);
+        cudaEventRecord(ev.e[1], e.stream());
+        e.sync();
+        s->upload_ms = elapsed(ev.e[0], ev.e[1]);
+        e.set_masks(Wm, Hm);
+        e.set_penalties(alpha, beta);
+        e.set_inner(inner_max_iter, inner_rel_tol);
+        *out = s.release();
+        return NNLM_OK;
+    });
+}
+
+int nnlm_synth_block(double* A, int64_t n_global, int64_t row0, int64_t nr, int64_t col0, int64_t mc, int32_t k,
+                     uint64_t seed_base, double noise, double na_frac, char* err, size_t errlen)
+{
+    return guarded(err, errlen, [&]() -> int {
+        NNLM_REQUIRE(A && n_global > 0 && nr > 0 && mc > 0 && k > 0, "nnlm_synth_block: bad argument");
+        DevBuf<double> dA((size_t)nr * mc);
+        launch_synth_block(dA.p, n_global, row0, nr, col0, mc, k, seed_base, noise, na_frac, 0);
+        NNLM_CUDA_CHECK(cudaMemcpy(A, dA.p, dA.bytes(), cudaMemcpyDeviceToHost));
         return NNLM_OK;
     });
 }

@@ -56,6 +56,7 @@ void check(int rc, const char* what)
 constexpr int kNcclFloat64 = 8;   // ncclDouble
 constexpr int kNcclUint64 = 5;    // ncclUint64
 constexpr int kNcclSum = 0;       // ncclSum
+constexpr int kNcclMax = 2;       // ncclMax
 
 }  // namespace
 
@@ -78,6 +79,11 @@ void Comm::allreduce_sum_f64(double* buf, size_t count, cudaStream_t st)
 void Comm::allreduce_sum_u64(unsigned long long* buf, size_t count, cudaStream_t st)
 {
     check(api().AllReduce(buf, buf, count, kNcclUint64, kNcclSum, comm_, st), "ncclAllReduce");
+}
+
+void Comm::allreduce_max_u64(unsigned long long* buf, size_t count, cudaStream_t st)
+{
+    check(api().AllReduce(buf, buf, count, kNcclUint64, kNcclMax, comm_, st), "ncclAllReduce");
 }
 
 void Comm::allgather_f64(const double* send, double* recv, size_t count_per_rank, cudaStream_t st)

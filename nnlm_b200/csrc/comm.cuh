@@ -17,6 +17,7 @@ public:
     int nranks() const { return nranks_; }
     void allreduce_sum_f64(double* buf, size_t count, cudaStream_t st);
     void allreduce_sum_u64(unsigned long long* buf, size_t count, cudaStream_t st);
+    void allreduce_max_u64(unsigned long long* buf, size_t count, cudaStream_t st);
     void allgather_f64(const double* send, double* recv, size_t count_per_rank, cudaStream_t st);
     void broadcast_f64(double* buf, size_t count, int root, cudaStream_t st);
 private:

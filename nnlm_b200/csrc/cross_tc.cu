@@ -431,10 +431,12 @@ k_split_matrix(const double* __restrict__ A, int64_t len, int64_t ncol, const do
         double a = nanv;
         if (i < len && j < ncol) {
             a = A[i + len * j];
-            __half h = __float2half_rn(0.f), l = h;
-            if (!is_missing(a)) split2((a - colmean[j]) * s, h, l);
-            a_hi[i + ld_a * j] = h;
-            a_lo[i + ld_a * j] = l;
+            if (a_hi) {
+                __half h = __float2half_rn(0.f), l = h;
+                if (!is_missing(a)) split2((a - colmean[j]) * s, h, l);
+                a_hi[i + ld_a * j] = h;
+                a_lo[i + ld_a * j] = l;
+            }
         }
         tile[r][tx] = a;
     }
@@ -557,20 +559,27 @@ void launch_cross_tc(const CrossPlan& plan, const __half* a_hi, const __half* a_
 
 void launch_means(const double* A, int64_t len, int64_t ncol, double* colmean, double* rowmean, cudaStream_t st)
 {
-    k_col_means<<<(int)std::min<int64_t>(ceil_div(ncol * 32, 256), 148 * 8), 256, 0, st>>>(A, len, ncol, colmean);
-    NNLM_LAUNCHED();
+    if (colmean) {
+        k_col_means<<<(int)std::min<int64_t>(ceil_div(ncol * 32, 256), 148 * 8), 256, 0, st>>>(A, len, ncol, colmean);
+        NNLM_LAUNCHED();
+    }
     if (rowmean) {
         k_row_means<<<(unsigned)ceil_div(len, 128), 128, 0, st>>>(A, len, ncol, rowmean);
         NNLM_LAUNCHED();
     }
 }
 
-void launch_absmax_scale(const double* A, int64_t total, unsigned long long* scratch, double* sA, cudaStream_t st)
+void launch_absmax(const double* A, int64_t total, unsigned long long* maxbits, cudaStream_t st)
 {
-    NNLM_CUDA_CHECK(cudaMemsetAsync(scratch, 0, sizeof(unsigned long long), st));
-    k_absmax<<<(int)std::min<int64_t>(ceil_div(total, 1024), 148 * 8), 1024, 0, st>>>(A, total, scratch);
+    NNLM_CUDA_CHECK(cudaMemsetAsync(maxbits, 0, sizeof(unsigned long long), st));
+    if (total <= 0) return;
+    k_absmax<<<(int)std::min<int64_t>(ceil_div(total, 1024), 148 * 8), 1024, 0, st>>>(A, total, maxbits);
     NNLM_LAUNCHED();
-    k_scale_from_max<<<1, 1, 0, st>>>(scratch, sA);
+}
+
+void launch_scale_from_max(const unsigned long long* maxbits, double* sA, cudaStream_t st)
+{
+    k_scale_from_max<<<1, 1, 0, st>>>(maxbits, sA);
     NNLM_LAUNCHED();
 }
 

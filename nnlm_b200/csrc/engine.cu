@@ -54,8 +54,8 @@ void KernelTimer::collect()
     spans_.clear();
 }
 
-Engine::Engine(int64_t n, int64_t m, int k, int method, int precision, int device, bool both_sides)
-    : n_(n), m_(m), k_(k), method_(method), device_(device), both_sides_(both_sides)
+Engine::Engine(int64_t n, int64_t m, int k, int method, int precision, int device, bool both_sides, Comm* comm)
+    : n_(n), m_(m), k_(k), method_(method), device_(device), both_sides_(both_sides), comm_(comm)
 {
     NNLM_REQUIRE(n > 0 && m > 0, "A must have positive dimensions");
     NNLM_REQUIRE(k >= 1, "rank k must be positive");
@@ -63,12 +63,19 @@ Engine::Engine(int64_t n, int64_t m, int k, int method, int precision, int devic
     if (method <= 2) NNLM_REQUIRE(k <= 128, "square-loss solvers support rank k <= 128");
     if (device_ < 0) NNLM_CUDA_CHECK(cudaGetDevice(&device_));
     NNLM_CUDA_CHECK(cudaSetDevice(device_));
+    const int R = comm_ ? comm_->nranks() : 1, rank = comm_ ? comm_->rank() : 0;
+    NNLM_REQUIRE(n >= R && m >= R, "fewer rows or columns than ranks");
+    chunk_n_ = ceil_div(n_, R); chunk_m_ = ceil_div(m_, R);
+    r0_ = std::min<int64_t>(n_, rank * chunk_n_); nr_ = std::min<int64_t>(n_, r0_ + chunk_n_) - r0_;
+    c0_ = std::min<int64_t>(m_, rank * chunk_m_); mc_ = std::min<int64_t>(m_, c0_ + chunk_m_) - c0_;
     // precision policy (include/nnlm_b200.h): the resident copies of A are fp64 unless the fast path is requested
     precision_req_ = precision;
-    storage_ = (precision == NNLM_PREC_FAST) ? Storage::F32 : Storage::F64;       // refined in ingest_device_A
+    storage_ = (precision == NNLM_PREC_FAST) ? Storage::F32 : Storage::F64;       // refined in ingest_shards
     NNLM_CUDA_CHECK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
-    Wt_.alloc((size_t)k_ * n_);
-    H_.alloc((size_t)k_ * m_);
+    Wt_.alloc((size_t)k_ * chunk_n_ * R);
+    H_.alloc((size_t)k_ * chunk_m_ * R);
+    NNLM_CUDA_CHECK(cudaMemsetAsync(Wt_.p, 0, Wt_.bytes(), st_));
+    NNLM_CUDA_CHECK(cudaMemsetAsync(H_.p, 0, H_.bytes(), st_));
     ensure_scratch();
 }
 
@@ -85,27 +92,26 @@ void Engine::ensure_scratch()
     Graw_.alloc((size_t)k_ * k_);
     sumY_.alloc(k_);
     if (method_ <= 2) {
-        size_t q = (size_t)cross_simt_splits(k_, n_, m_) * k_ * m_;
-        if (both_sides_) q = std::max(q, (size_t)cross_simt_splits(k_, m_, n_) * k_ * n_);
+        size_t q = (size_t)cross_simt_splits(k_, n_, mc_) * k_ * std::max<int64_t>(mc_, 1);
+        if (both_sides_) q = std::max(q, (size_t)cross_simt_splits(k_, m_, nr_) * k_ * std::max<int64_t>(nr_, 1));
         if (cross_tc_supported(k_)) {
-            plan_h_ = cross_tc_plan(k_, n_, m_);
-            q = std::max(q, (size_t)plan_h_.slots * k_ * m_);
-            if (both_sides_) {
-                plan_w_ = cross_tc_plan(k_, m_, n_);
-                q = std::max(q, (size_t)plan_w_.slots * k_ * n_);
-            }
+            if (mc_ > 0) { plan_h_ = cross_tc_plan(k_, n_, mc_); q = std::max(q, (size_t)plan_h_.slots * k_ * mc_); }
+            if (both_sides_ && nr_ > 0) { plan_w_ = cross_tc_plan(k_, m_, nr_); q = std::max(q, (size_t)plan_w_.slots * k_ * nr_); }
         }
         Qp_.alloc(q);
     } else {
         Yr_.alloc((size_t)k_ * big);
-        size_t w = solve_kl_scratch_doubles(n_, m_);
-        if (both_sides_) w = std::max(w, solve_kl_scratch_doubles(m_, n_));
+        size_t w = solve_kl_scratch_doubles(n_, mc_);
+        if (both_sides_) w = std::max(w, solve_kl_scratch_doubles(m_, nr_));
         if (w) wh_.alloc(w);
     }
-    size_t rp = std::max<size_t>((size_t)ingest_part_count(n_, m_) * 2, (size_t)error_part_count(n_, m_) * 2);
+    size_t rp = std::max<size_t>((size_t)ingest_part_count(n_, std::max<int64_t>(mc_, 1)) * 2,
+                                 (size_t)error_part_count(n_, std::max<int64_t>(mc_, 1)) * 2);
+    if (both_sides_) rp = std::max<size_t>(rp, (size_t)ingest_part_count(std::max<int64_t>(nr_, 1), m_) * 2);
     rp = std::max<size_t>(rp, (size_t)stats_part_count(big) * 3);
     red_part_.alloc(rp);
     small_.alloc(16);
+    tpc_scratch_.alloc(scd_tpc_scratch_doubles());
     sweeps_.alloc(1);
     host_small_.alloc(16);
     NNLM_CUDA_CHECK(cudaMemsetAsync(sweeps_.p, 0, sizeof(unsigned long long), st_));
@@ -116,26 +122,35 @@ void Engine::sync() { NNLM_CUDA_CHECK(cudaStreamSynchronize(st_)); timer.collect
 void Engine::upload_A(const double* A)
 {
     DeviceGuard g(device_);
+    NNLM_REQUIRE(comm_ == nullptr, "upload_A takes the whole matrix: use ingest_shards on the sharded path");
     const size_t cnt = (size_t)n_ * m_;
-    A64_.alloc(cnt);
-    NNLM_CUDA_CHECK(cudaMemcpyAsync(A64_.p, A, cnt * sizeof(double), cudaMemcpyHostToDevice, st_));
+    DevBuf<double> dA(cnt);
+    NNLM_CUDA_CHECK(cudaMemcpyAsync(dA.p, A, cnt * sizeof(double), cudaMemcpyHostToDevice, st_));
     h2d_bytes += cnt * sizeof(double);
-    ingest_device_A(nullptr);
+    if (precision_req_ != NNLM_PREC_FAST) {          // fp64 storage keeps the uploaded buffer as the column copy
+        A64_ = std::move(dA);
+        ingest_shards(nullptr, both_sides_ ? A64_.p : nullptr);
+    } else {
+        ingest_shards(dA.p, both_sides_ ? dA.p : nullptr);
+    }
 }
 
-void Engine::ingest_device_A(const double* dA)
+// dAcol == nullptr means "A64_ already holds the column copy"
+void Engine::ingest_shards(const double* dAcol, const double* dArow)
 {
     DeviceGuard g(device_);
-    const size_t cnt = (size_t)n_ * m_;
-    if (dA) {
-        A64_.alloc(cnt);
-        NNLM_CUDA_CHECK(cudaMemcpyAsync(A64_.p, dA, cnt * sizeof(double), cudaMemcpyDeviceToDevice, st_));
+    const size_t cnt_c = (size_t)n_ * mc_, cnt_r = (size_t)nr_ * m_;
+    if (!dAcol) dAcol = A64_.p;
+    NNLM_REQUIRE(!both_sides_ || dArow != nullptr, "the row shard of A is required when both halves run");
+    // pass 1: missing-entry count and the constant part of the KL distance (src/nnmf.cpp:64-73), over the column shards
+    double* acc = small_.p;
+    NNLM_CUDA_CHECK(cudaMemsetAsync(acc, 0, 2 * sizeof(double), st_));
+    if (mc_ > 0) {
+        launch_ingest<double>(dAcol, n_, mc_, 0, mc_, nullptr, nullptr, red_part_.p, st_);
+        launch_reduce_partials(red_part_.p, ingest_part_count(n_, mc_), 2, acc, st_);
     }
-    const int64_t parts = ingest_part_count(n_, m_);
-    // pass 1: missing-entry count and the constant part of the KL distance (src/nnmf.cpp:64-73)
-    launch_ingest<double>(A64_.p, n_, m_, 0, m_, nullptr, nullptr, red_part_.p, st_);
-    launch_reduce_partials(red_part_.p, parts, 2, small_.p, st_);
-    NNLM_CUDA_CHECK(cudaMemcpyAsync(host_small_.p, small_.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    if (comm_) comm_->allreduce_sum_f64(acc, 2, st_);
+    NNLM_CUDA_CHECK(cudaMemcpyAsync(host_small_.p, acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st_));
     sync();
     d2h_bytes += 2 * sizeof(double);
     kl_const_sum_ = host_small_.p[0];
@@ -144,38 +159,49 @@ void Engine::ingest_device_A(const double* dA)
     if (precision_req_ == NNLM_PREC_FAST && method_ <= 2 && cross_tc_supported(k_) && !use_missing_path())
         storage_ = Storage::F16X2;
     if (storage_ == Storage::F64) {
-        if (both_sides_) {
-            At64_.alloc(cnt);
-            launch_ingest<double>(A64_.p, n_, m_, 0, m_, nullptr, At64_.p, red_part_.p, st_);
+        if (dAcol != A64_.p) {
+            A64_.alloc(cnt_c);
+            NNLM_CUDA_CHECK(cudaMemcpyAsync(A64_.p, dAcol, cnt_c * sizeof(double), cudaMemcpyDeviceToDevice, st_));
+        }
+        if (both_sides_ && nr_ > 0) {
+            At64_.alloc(cnt_r);
+            launch_ingest<double>(dArow, nr_, m_, 0, m_, nullptr, At64_.p, red_part_.p, st_);
         }
     } else if (storage_ == Storage::F32) {
-        A32_.alloc(cnt);
-        if (both_sides_) At32_.alloc(cnt);
-        launch_ingest<float>(A64_.p, n_, m_, 0, m_, A32_.p, both_sides_ ? At32_.p : nullptr, red_part_.p, st_);
+        A32_.alloc(cnt_c);
+        if (mc_ > 0) launch_ingest<float>(dAcol, n_, mc_, 0, mc_, A32_.p, nullptr, red_part_.p, st_);
+        if (both_sides_ && nr_ > 0) {
+            At32_.alloc(cnt_r);
+            launch_ingest<float>(dArow, nr_, m_, 0, m_, nullptr, At32_.p, red_part_.p, st_);
+        }
     } else {
         const int64_t ld_n = cross_tc_ld(n_), ld_m = cross_tc_ld(m_);
         const int np = cross_tc_np(k_);
-        a_hi_.alloc((size_t)ld_n * m_); a_lo_.alloc((size_t)ld_n * m_);
-        if (both_sides_) { t_hi_.alloc((size_t)ld_m * n_); t_lo_.alloc((size_t)ld_m * n_); }
+        scale_a_.alloc(1); fscales_.alloc(np); unscale_.alloc(np); rowmax_.alloc(np + 1);
         const int64_t ld_f = std::max(ld_n, both_sides_ ? ld_m : (int64_t)0);
         f_hi_.alloc((size_t)np * ld_f); f_lo_.alloc((size_t)np * ld_f);
-        scale_a_.alloc(1); fscales_.alloc(np); unscale_.alloc(np); rowmax_.alloc(np + 1);
-        // pitch padding of the planes must read as zero (it is never written by the conversion kernels)
-        NNLM_CUDA_CHECK(cudaMemsetAsync(a_hi_.p, 0, a_hi_.bytes(), st_));
-        NNLM_CUDA_CHECK(cudaMemsetAsync(a_lo_.p, 0, a_lo_.bytes(), st_));
-        if (both_sides_) {
+        // one power-of-two scale for the whole matrix: max |A| over all shards
+        launch_absmax(dAcol, (int64_t)cnt_c, rowmax_.p + np, st_);
+        if (comm_) comm_->allreduce_max_u64(rowmax_.p + np, 1, st_);
+        launch_scale_from_max(rowmax_.p + np, scale_a_.p, st_);
+        if (mc_ > 0) {
+            a_hi_.alloc((size_t)ld_n * mc_); a_lo_.alloc((size_t)ld_n * mc_); colmean_.alloc(mc_);
+            // pitch padding of the planes must read as zero (it is never written by the conversion kernels)
+            NNLM_CUDA_CHECK(cudaMemsetAsync(a_hi_.p, 0, a_hi_.bytes(), st_));
+            NNLM_CUDA_CHECK(cudaMemsetAsync(a_lo_.p, 0, a_lo_.bytes(), st_));
+            launch_means(dAcol, n_, mc_, colmean_.p, nullptr, st_);
+            launch_split_matrix(dAcol, n_, mc_, scale_a_.p, colmean_.p, nullptr, a_hi_.p, a_lo_.p, ld_n, nullptr, nullptr, 0, st_);
+            // the error evaluation (trace iterations only) reads an fp32 copy of the column shard
+            A32_.alloc(cnt_c);
+            launch_ingest<float>(dAcol, n_, mc_, 0, mc_, A32_.p, nullptr, red_part_.p, st_);
+        }
+        if (both_sides_ && nr_ > 0) {
+            t_hi_.alloc((size_t)ld_m * nr_); t_lo_.alloc((size_t)ld_m * nr_); rowmean_.alloc(nr_);
             NNLM_CUDA_CHECK(cudaMemsetAsync(t_hi_.p, 0, t_hi_.bytes(), st_));
             NNLM_CUDA_CHECK(cudaMemsetAsync(t_lo_.p, 0, t_lo_.bytes(), st_));
+            launch_means(dArow, nr_, m_, nullptr, rowmean_.p, st_);
+            launch_split_matrix(dArow, nr_, m_, scale_a_.p, nullptr, rowmean_.p, nullptr, nullptr, 0, t_hi_.p, t_lo_.p, ld_m, st_);
         }
-        colmean_.alloc(m_);
-        if (both_sides_) rowmean_.alloc(n_);
-        launch_means(A64_.p, n_, m_, colmean_.p, both_sides_ ? rowmean_.p : nullptr, st_);
-        launch_absmax_scale(A64_.p, (int64_t)cnt, rowmax_.p + np, scale_a_.p, st_);
-        launch_split_matrix(A64_.p, n_, m_, scale_a_.p, colmean_.p, both_sides_ ? rowmean_.p : nullptr, a_hi_.p, a_lo_.p, ld_n,
-                            both_sides_ ? t_hi_.p : nullptr, both_sides_ ? t_lo_.p : nullptr, ld_m, st_);
-        // the error evaluation (trace iterations only) reads an fp32 copy of A
-        A32_.alloc(cnt);
-        launch_ingest<float>(A64_.p, n_, m_, 0, m_, A32_.p, nullptr, red_part_.p, st_);
     }
     sync();
     if (storage_ != Storage::F64) A64_.release();
@@ -187,18 +213,18 @@ void Engine::set_factors(const double* W, const double* H)
     DevBuf<double> tmp((size_t)n_ * k_);
     NNLM_CUDA_CHECK(cudaMemcpyAsync(tmp.p, W, tmp.bytes(), cudaMemcpyHostToDevice, st_));
     launch_transpose_d(tmp.p, n_, k_, Wt_.p, st_);                          // inplace_trans(W), src/nnmf.cpp:90
-    NNLM_CUDA_CHECK(cudaMemcpyAsync(H_.p, H, H_.bytes(), cudaMemcpyHostToDevice, st_));
+    NNLM_CUDA_CHECK(cudaMemcpyAsync(H_.p, H, sizeof(double) * k_ * m_, cudaMemcpyHostToDevice, st_));
     sync();
-    h2d_bytes += tmp.bytes() + H_.bytes();
+    h2d_bytes += tmp.bytes() + sizeof(double) * k_ * m_;
 }
 
 void Engine::set_factors_t(const double* Wt, const double* H)
 {
     DeviceGuard g(device_);
-    NNLM_CUDA_CHECK(cudaMemcpyAsync(Wt_.p, Wt, Wt_.bytes(), cudaMemcpyHostToDevice, st_));
-    NNLM_CUDA_CHECK(cudaMemcpyAsync(H_.p, H, H_.bytes(), cudaMemcpyHostToDevice, st_));
+    NNLM_CUDA_CHECK(cudaMemcpyAsync(Wt_.p, Wt, sizeof(double) * k_ * n_, cudaMemcpyHostToDevice, st_));
+    NNLM_CUDA_CHECK(cudaMemcpyAsync(H_.p, H, sizeof(double) * k_ * m_, cudaMemcpyHostToDevice, st_));
     sync();
-    h2d_bytes += Wt_.bytes() + H_.bytes();
+    h2d_bytes += sizeof(double) * k_ * (n_ + m_);
 }
 
 void Engine::get_factors(double* W, double* H)
@@ -207,17 +233,17 @@ void Engine::get_factors(double* W, double* H)
     DevBuf<double> tmp((size_t)n_ * k_);
     launch_transpose_d(Wt_.p, k_, n_, tmp.p, st_);                          // W.t(), src/nnmf.cpp:212
     NNLM_CUDA_CHECK(cudaMemcpyAsync(W, tmp.p, tmp.bytes(), cudaMemcpyDeviceToHost, st_));
-    NNLM_CUDA_CHECK(cudaMemcpyAsync(H, H_.p, H_.bytes(), cudaMemcpyDeviceToHost, st_));
+    NNLM_CUDA_CHECK(cudaMemcpyAsync(H, H_.p, sizeof(double) * k_ * m_, cudaMemcpyDeviceToHost, st_));
     sync();
-    d2h_bytes += tmp.bytes() + H_.bytes();
+    d2h_bytes += tmp.bytes() + sizeof(double) * k_ * m_;
 }
 
 void Engine::get_H(double* H)
 {
     DeviceGuard g(device_);
-    NNLM_CUDA_CHECK(cudaMemcpyAsync(H, H_.p, H_.bytes(), cudaMemcpyDeviceToHost, st_));
+    NNLM_CUDA_CHECK(cudaMemcpyAsync(H, H_.p, sizeof(double) * k_ * m_, cudaMemcpyDeviceToHost, st_));
     sync();
-    d2h_bytes += H_.bytes();
+    d2h_bytes += sizeof(double) * k_ * m_;
 }
 
 void Engine::set_masks(const int32_t* Wm, const int32_t* Hm)
@@ -248,6 +274,37 @@ void Engine::set_penalties(const double* alpha, const double* beta)
     for (int i = 0; i < 3; i++) { alpha_[i] = alpha ? alpha[i] : 0.0; beta_[i] = beta ? beta[i] : 0.0; }
 }
 
+// The Gram of the fixed factor (src/update_with_missing.cpp:19): each rank forms the Gram of the slice it solved in the
+// previous half, the k x k partials are all-reduced (the one exchange BASELINE.json's north star names), then regularised.
+void Engine::shared_gram(const Half& h, bool raw_only)
+{
+    timer.begin(KernelTimer::GRAM, st_);
+    launch_gram(h.Yloc, k_, h.len_loc, nullptr, gram_part_.p, Graw_.p, st_);
+    timer.end(st_);
+    if (comm_) {
+        timer.begin(KernelTimer::COMM, st_);
+        comm_->allreduce_sum_f64(Graw_.p, (size_t)k_ * k_, st_);
+        comm_bytes += sizeof(double) * k_ * k_;
+        timer.end(st_);
+    }
+    if (!raw_only) launch_gram_regularise(Graw_.p, k_, h.pen, G_.p, st_);                 // update_with_missing.cpp:20-24
+}
+
+void Engine::solve_dense_ls(const Half& h, int splits)
+{
+    shared_gram(h, false);
+    timer.begin(KernelTimer::SOLVE, st_);
+    if (h.ncol > 0) {
+        if (method_ == 1 && scd_tpc_supported(k_))
+            launch_scd_tpc(h.X, G_.p, Qp_.p, splits, h.mask, k_, h.ncol, h.pen[2], inner_max_iter_, inner_rel_tol_, sweeps_.p,
+                           tpc_scratch_.p, st_);
+        else
+            launch_solve_ls(method_, h.X, G_.p, Qp_.p, splits, h.mask, k_, h.ncol, h.pen[2], inner_max_iter_, inner_rel_tol_,
+                            sweeps_.p, st_);
+    }
+    timer.end(st_);
+}
+
 template <typename TA>
 void Engine::run_half_t(const Half& h)
 {
@@ -256,14 +313,12 @@ void Engine::run_half_t(const Half& h)
     if (method_ <= 2) {
         const int splits = cross_simt_splits(k_, h.len, h.ncol);
         timer.begin(KernelTimer::CROSS, st_);
-        launch_cross_simt<TA>(h.Y, A, k_, h.len, h.ncol, splits, Qp_.p, st_);
+        if (h.ncol > 0) launch_cross_simt<TA>(h.Y, A, k_, h.len, h.ncol, splits, Qp_.p, st_);
         timer.end(st_);
         if (!missing) {
             solve_dense_ls(h, splits);
         } else {
-            timer.begin(KernelTimer::GRAM, st_);
-            launch_gram(h.Y, k_, h.len, nullptr, gram_part_.p, Graw_.p, st_);
-            timer.end(st_);
+            shared_gram(h, true);
             timer.begin(KernelTimer::SOLVE, st_);
             launch_solve_ls_missing<TA>(method_, h.X, h.Y, A, Graw_.p, Qp_.p, splits, h.mask, k_, h.len, h.ncol, h.pen,
                                         inner_max_iter_, inner_rel_tol_, sweeps_.p, st_);
@@ -281,61 +336,63 @@ void Engine::run_half_t(const Half& h)
     }
 }
 
-void Engine::solve_dense_ls(const Half& h, int splits)
+void Engine::run_half_tc(const Half& h)
 {
-    timer.begin(KernelTimer::GRAM, st_);
-    launch_gram(h.Y, k_, h.len, h.pen, gram_part_.p, G_.p, st_);                          // update_with_missing.cpp:19-24
-    timer.end(st_);
-    timer.begin(KernelTimer::SOLVE, st_);
-    if (method_ == 1 && scd_tpc_supported(k_))
-        launch_scd_tpc(h.X, G_.p, Qp_.p, splits, h.mask, k_, h.ncol, h.pen[2], inner_max_iter_, inner_rel_tol_, sweeps_.p, st_);
-    else
-        launch_solve_ls(method_, h.X, G_.p, Qp_.p, splits, h.mask, k_, h.ncol, h.pen[2], inner_max_iter_, inner_rel_tol_,
-                        sweeps_.p, st_);
-    timer.end(st_);
-}
-
-void Engine::run_half_tc(const Half& h, bool w_side)
-{
-    const CrossPlan& plan = w_side ? plan_w_ : plan_h_;
-    timer.begin(KernelTimer::GRAM, st_);
-    launch_split_factor(h.Y, k_, h.len, plan.ld_f, plan.np, scale_a_.p, rowmax_.p, fscales_.p, unscale_.p, f_hi_.p, f_lo_.p, st_);
-    launch_rowsum(h.Y, k_, h.len, gram_part_.p, sumY_.p, st_);
-    timer.end(st_);
-    timer.begin(KernelTimer::CROSS, st_);
-    launch_cross_tc(plan, w_side ? t_hi_.p : a_hi_.p, w_side ? t_lo_.p : a_lo_.p, f_hi_.p, f_lo_.p, unscale_.p,
-                    w_side ? rowmean_.p : colmean_.p, sumY_.p, Qp_.p, st_);
-    timer.end(st_);
+    const CrossPlan& plan = h.w_side ? plan_w_ : plan_h_;
+    if (h.ncol > 0) {
+        timer.begin(KernelTimer::GRAM, st_);
+        launch_split_factor(h.Y, k_, h.len, plan.ld_f, plan.np, scale_a_.p, rowmax_.p, fscales_.p, unscale_.p, f_hi_.p, f_lo_.p, st_);
+        launch_rowsum(h.Y, k_, h.len, gram_part_.p, sumY_.p, st_);
+        timer.end(st_);
+        timer.begin(KernelTimer::CROSS, st_);
+        launch_cross_tc(plan, h.w_side ? t_hi_.p : a_hi_.p, h.w_side ? t_lo_.p : a_lo_.p, f_hi_.p, f_lo_.p, unscale_.p,
+                        h.w_side ? rowmean_.p : colmean_.p, sumY_.p, Qp_.p, st_);
+        timer.end(st_);
+    }
     solve_dense_ls(h, plan.slots);
 }
 
 void Engine::run_half(const Half& h)
 {
     DeviceGuard g(device_);
-    if (storage_ == Storage::F64) run_half_t<double>(h);
+    if (storage_ == Storage::F16X2) run_half_tc(h);
+    else if (storage_ == Storage::F64) run_half_t<double>(h);
     else run_half_t<float>(h);
+}
+
+// all-gather of the slices every rank just solved (in place: rank g's slice sits at g * chunk_cols columns)
+void Engine::gather(double* full, int64_t chunk_cols)
+{
+    if (!comm_) return;
+    timer.begin(KernelTimer::COMM, st_);
+    const size_t cnt = (size_t)k_ * chunk_cols;
+    comm_->allgather_f64(full + (size_t)comm_->rank() * cnt, full, cnt, st_);
+    comm_bytes += sizeof(double) * cnt * (comm_->nranks() - 1);
+    timer.end(st_);
 }
 
 void Engine::half_w()
 {
     NNLM_REQUIRE(both_sides_, "this engine was created for the H-half only");
     const void* At = storage_ == Storage::F64 ? (const void*)At64_.p : (const void*)At32_.p;
-    const Half h{Wt_.p, n_, H_.p, m_, At, has_wm_ ? Wm_.p : nullptr, alpha_};
-    if (storage_ == Storage::F16X2) { DeviceGuard g(device_); run_half_tc(h, true); }
-    else run_half(h);
+    // solve W[:, rows of this rank] given the whole H; the Gram partial is over the H columns this rank solved last
+    run_half(Half{Wt_.p + (size_t)k_ * r0_, nr_, H_.p, m_, H_.p + (size_t)k_ * c0_, mc_, At,
+                  has_wm_ ? Wm_.p + (size_t)k_ * r0_ : nullptr, alpha_, true});
+    gather(Wt_.p, chunk_n_);
 }
 
 void Engine::half_h()
 {
     const void* A = storage_ == Storage::F64 ? (const void*)A64_.p : (const void*)A32_.p;
-    const Half h{H_.p, m_, Wt_.p, n_, A, has_hm_ ? Hm_.p : nullptr, beta_};
-    if (storage_ == Storage::F16X2) { DeviceGuard g(device_); run_half_tc(h, false); }
-    else run_half(h);
+    run_half(Half{H_.p + (size_t)k_ * c0_, mc_, Wt_.p, n_, Wt_.p + (size_t)k_ * r0_, nr_, A,
+                  has_hm_ ? Hm_.p + (size_t)k_ * c0_ : nullptr, beta_, false});
+    gather(H_.p, chunk_m_);
 }
 
 void Engine::cross_only(double* Q_host)
 {
     DeviceGuard g(device_);
+    NNLM_REQUIRE(comm_ == nullptr, "cross_only is a single-GPU diagnostic");
     int splits;
     if (storage_ == Storage::F16X2) {
         launch_split_factor(Wt_.p, k_, n_, plan_h_.ld_f, plan_h_.np, scale_a_.p, rowmax_.p, fscales_.p, unscale_.p, f_hi_.p, f_lo_.p, st_);
@@ -362,10 +419,17 @@ void Engine::cross_only(double* Q_host)
 void Engine::errors(ErrorTerms* out)
 {
     DeviceGuard g(device_);
-    if (storage_ == Storage::F64) launch_error<double>(A64_.p, Wt_.p, H_.p, k_, n_, m_, red_part_.p, small_.p, st_);
-    else launch_error<float>(A32_.p, Wt_.p, H_.p, k_, n_, m_, red_part_.p, small_.p, st_);
+    timer.begin(KernelTimer::ERROR, st_);
+    NNLM_CUDA_CHECK(cudaMemsetAsync(small_.p, 0, 2 * sizeof(double), st_));
+    if (mc_ > 0) {
+        // this rank's columns of A against the whole W and its columns of H
+        if (storage_ == Storage::F64) launch_error<double>(A64_.p, Wt_.p, H_.p + (size_t)k_ * c0_, k_, n_, mc_, red_part_.p, small_.p, st_);
+        else launch_error<float>(A32_.p, Wt_.p, H_.p + (size_t)k_ * c0_, k_, n_, mc_, red_part_.p, small_.p, st_);
+    }
+    if (comm_) comm_->allreduce_sum_f64(small_.p, 2, st_);
     launch_factor_stats(Wt_.p, k_, n_, red_part_.p, small_.p + 2, st_);
     launch_factor_stats(H_.p, k_, m_, red_part_.p, small_.p + 5, st_);
+    timer.end(st_);
     NNLM_CUDA_CHECK(cudaMemcpyAsync(host_small_.p, small_.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, st_));
     sync();
     d2h_bytes += 8 * sizeof(double);
@@ -378,6 +442,7 @@ uint64_t Engine::take_sweeps()
 {
     DeviceGuard g(device_);
     unsigned long long* hp = reinterpret_cast<unsigned long long*>(host_small_.p + 12);
+    if (comm_) comm_->allreduce_sum_u64(sweeps_.p, 1, st_);
     NNLM_CUDA_CHECK(cudaMemcpyAsync(hp, sweeps_.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st_));
     NNLM_CUDA_CHECK(cudaMemsetAsync(sweeps_.p, 0, sizeof(unsigned long long), st_));
     sync();

@@ -7,9 +7,18 @@
 // The reference materialises A.t() every iteration; here the transposed copy is made once at upload (ingest.cu) and both
 // copies stay resident in HBM (2 x n*m*elt bytes), so each half streams its own copy with unit stride along the
 // contraction index.
+//
+// Sharding (one process per GPU). Rank g of R owns the columns [c0, c0+mc) of A for the H-half (columns
+// of H are independent given W) and the rows [r0, r0+nr) of A for the W-half (rows of W are independent given H); its
+// "column copy" is A[:, cols_g] and its "row copy" is A[rows_g, :]' — together 2 x n*m/R elements, the same footprint
+// per GPU as the single-GPU layout divided by R. Every cross-product entry is formed entirely on one GPU. Exchanges per
+// half-iteration: one all-reduce of the k x k Gram of the slice each rank just solved, and one all-gather of the solved
+// factor slices (k x n or k x m doubles in total) so the next half sees the whole fixed factor. With R = 1 all of this
+// degenerates to the single-GPU path (no communicator).
 #pragma once
 #include <vector>
 
+#include "comm.cuh"
 #include "kernels.cuh"
 
 namespace nnlm {
@@ -27,15 +36,15 @@ struct ErrorTerms {     // raw sums, all fp64
 // cross-product and solver launches; accumulated at collect().
 class KernelTimer {
 public:
-    enum Cat { CROSS = 0, SOLVE = 1, GRAM = 2, ERROR = 3, NCAT = 4 };
+    enum Cat { CROSS = 0, SOLVE = 1, GRAM = 2, ERROR = 3, COMM = 4, NCAT = 5 };
     ~KernelTimer();
     void enable(bool on) { on_ = on; }
     bool enabled() const { return on_; }
     void begin(Cat c, cudaStream_t st);
     void end(cudaStream_t st);
     void collect();                       // stream must be synchronised
-    double ms[NCAT] = {0, 0, 0, 0};
-    uint64_t count[NCAT] = {0, 0, 0, 0};
+    double ms[NCAT] = {0, 0, 0, 0, 0};
+    uint64_t count[NCAT] = {0, 0, 0, 0, 0};
     void reset() { for (int i = 0; i < NCAT; i++) { ms[i] = 0; count[i] = 0; } }
 private:
     struct Span { cudaEvent_t a, b; Cat c; };
@@ -50,17 +59,25 @@ private:
 class Engine {
 public:
     KernelTimer timer;
-    // both_sides = false: only the H-half will run (nnlm_update / nnlm_nnlm), no transposed copy of A is kept
-    Engine(int64_t n, int64_t m, int k, int method, int precision, int device, bool both_sides = true);
+    // n, m: GLOBAL dimensions of A. both_sides = false: only the H-half will run (nnlm_update / nnlm_nnlm), no row copy
+    // of A is kept. comm: communicator of the column/row-sharded path, or nullptr for one GPU.
+    Engine(int64_t n, int64_t m, int k, int method, int precision, int device, bool both_sides = true, Comm* comm = nullptr);
     ~Engine();
     Engine(const Engine&) = delete;
     Engine& operator=(const Engine&) = delete;
 
-    // A: n x m column-major host doubles (borrowed for the duration of the call only)
+    // the shard of this rank (the whole matrix on one GPU)
+    int64_t row0() const { return r0_; }
+    int64_t rows_local() const { return nr_; }
+    int64_t col0() const { return c0_; }
+    int64_t cols_local() const { return mc_; }
+
+    // single GPU: A is the whole n x m column-major host matrix (borrowed for the duration of the call only)
     void upload_A(const double* A);
-    // A already on the device (n x m column-major fp64); consumed by the same ingest pass
-    void ingest_device_A(const double* dA);
-    void set_factors(const double* W /*n x k*/, const double* H /*k x m*/);
+    // device-resident shards (fp64, column-major): Acol = A[:, col0 .. col0+mc) (n x mc), Arow = A[row0 .. row0+nr, :]
+    // (nr x m, may be nullptr when both_sides is false). On one GPU both may point to the same n x m matrix.
+    void ingest_shards(const double* dAcol, const double* dArow);
+    void set_factors(const double* W /*n x k*/, const double* H /*k x m*/);      // whole factors, on every rank
     void get_factors(double* W, double* H);
     void set_factors_t(const double* Wt /*k x n*/, const double* H /*k x m*/);
     void get_H(double* H);
@@ -71,48 +88,50 @@ public:
     void set_penalties(const double* alpha, const double* beta);
     void set_inner(unsigned max_iter, double rel_tol) { inner_max_iter_ = max_iter; inner_rel_tol_ = rel_tol; }
 
-    void half_w();      // solve for W given H
-    void half_h();      // solve for H given W
-    // generic single half-iteration on explicit operands already on the device (nnlm_update / nnlm_nnlm)
-    void errors(ErrorTerms* out);                 // synchronises the stream
+    void half_w();      // solve for W given H (this rank's rows), then all-gather W
+    void half_h();      // solve for H given W (this rank's columns), then all-gather H
+    void errors(ErrorTerms* out);                 // global sums; synchronises the stream
     // diagnostic: Q = Wt * A (k x m, missing entries of A read as zero) through the cross-product path of the current storage
     void cross_only(double* Q_host);
-    uint64_t take_sweeps();                       // read and reset total_raw_iter (synchronises)
+    uint64_t take_sweeps();                       // read and reset the global total_raw_iter (synchronises)
     void sync();
 
     int64_t n() const { return n_; }
     int64_t m() const { return m_; }
     int k() const { return k_; }
     int method() const { return method_; }
+    int nranks() const { return comm_ ? comm_->nranks() : 1; }
     bool any_missing() const { return n_missing_ > 0; }
-    int64_t n_missing() const { return n_missing_; }
-    double kl_const_sum() const { return kl_const_sum_; }
+    int64_t n_missing() const { return n_missing_; }      // global
+    double kl_const_sum() const { return kl_const_sum_; } // global
     int precision_used() const { return storage_ == Storage::F64 ? NNLM_PREC_EXACT : NNLM_PREC_FAST; }
     cudaStream_t stream() const { return st_; }
     int device() const { return device_; }
-    uint64_t h2d_bytes = 0, d2h_bytes = 0;
-
-    // direct device access for the single-shot entry points
-    double* dWt() { return Wt_.p; }
-    double* dH() { return H_.p; }
+    uint64_t h2d_bytes = 0, d2h_bytes = 0, comm_bytes = 0;
 
 private:
     struct Half {
-        double* X; int64_t ncol;
-        const double* Y; int64_t len;
-        const void* A;
+        double* X; int64_t ncol;      // solved slice (k x ncol)
+        const double* Y; int64_t len; // fixed factor, whole (k x len)
+        const double* Yloc; int64_t len_loc;   // the slice of Y this rank solved in the previous half (Gram partial)
+        const void* A;                // len x ncol copy of A for this half (F64 / F32 storage)
         const uint8_t* mask;
         const double* pen;
+        bool w_side;
     };
     void run_half(const Half& h);
     template <typename TA> void run_half_t(const Half& h);
-    void run_half_tc(const Half& h, bool w_side);
+    void run_half_tc(const Half& h);
+    void shared_gram(const Half& h, bool raw_only);     // G_ (regularised) and Graw_ from the all-reduced slice Grams
     void solve_dense_ls(const Half& h, int splits);
+    void gather(double* full, int64_t chunk_cols);
     void ensure_scratch();
 
     int64_t n_, m_;
     int k_, method_, device_;
     bool both_sides_;
+    Comm* comm_;
+    int64_t chunk_n_, chunk_m_, r0_, nr_, c0_, mc_;
     int missing_mode_ = -1;
     Storage storage_;
     cudaStream_t st_ = nullptr;
@@ -120,22 +139,23 @@ private:
     double inner_rel_tol_ = 1e-9;
     double alpha_[3] = {0, 0, 0}, beta_[3] = {0, 0, 0};
 
-    DevBuf<double> A64_, At64_;     // n x m and m x n, column-major
+    DevBuf<double> A64_, At64_;     // column copy n x mc and row copy m x nr, column-major
     DevBuf<float> A32_, At32_;
-    // fp16 hi/lo planes for the tensor-core cross-product (cross_tc.cu): A as [m][ld(n)], A' as [n][ld(m)], factor [np][ld]
+    // fp16 hi/lo planes for the tensor-core cross-product (cross_tc.cu): column copy [mc][ld(n)], row copy [nr][ld(m)],
+    // factor [np][ld]
     DevBuf<__half> a_hi_, a_lo_, t_hi_, t_lo_, f_hi_, f_lo_;
     DevBuf<double> scale_a_, fscales_, unscale_, colmean_, rowmean_;
     DevBuf<unsigned long long> rowmax_;
     CrossPlan plan_h_, plan_w_;
     int precision_req_ = NNLM_PREC_AUTO;
-    DevBuf<double> Wt_, H_;         // k x n, k x m
+    DevBuf<double> Wt_, H_;         // whole factors, k x (chunk_n * R) and k x (chunk_m * R)
     DevBuf<uint8_t> Wm_, Hm_;       // k x n, k x m or empty
     bool has_wm_ = false, has_hm_ = false;
     int64_t n_missing_ = 0;
     double kl_const_sum_ = 0.0;
 
     // scratch
-    DevBuf<double> gram_part_, G_, Graw_, sumY_, Qp_, Yr_, wh_, red_part_, small_;   // small_: 16 doubles of results
+    DevBuf<double> gram_part_, G_, Graw_, sumY_, Qp_, Yr_, wh_, red_part_, small_, tpc_scratch_;   // small_: 16 doubles of results
     DevBuf<unsigned long long> sweeps_;
     PinnedBuf<double> host_small_;
 };

@@ -135,6 +135,24 @@ void launch_gram(const double* Y, int k, int64_t len, const double* pen, double*
     NNLM_LAUNCHED();
 }
 
+__global__ void k_gram_regularise(const double* __restrict__ Graw, int k, double b0, double b1, double* __restrict__ G)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= k * k) return;
+    double s = Graw[e];
+    const bool diag = (e / k) == (e % k);
+    if (b0 != b1 && diag) s += b0 - b1;
+    if (b1 != 0.0) s += b1;
+    if (diag) s += TINY_NUM;
+    G[e] = s;
+}
+
+void launch_gram_regularise(const double* Graw, int k, const double* pen, double* G, cudaStream_t st)
+{
+    k_gram_regularise<<<(k * k + 255) / 256, 256, 0, st>>>(Graw, k, pen[0], pen[1], G);
+    NNLM_LAUNCHED();
+}
+
 void launch_rowsum(const double* Y, int k, int64_t len, double* part, double* out, cudaStream_t st)
 {
     NNLM_REQUIRE(k >= 1 && k <= 256, "rank k must be in [1, 256]");

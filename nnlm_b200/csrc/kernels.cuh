@@ -39,12 +39,17 @@ void launch_uniform(double* out, int64_t count, uint64_t seed, uint64_t offset, 
 // NaN iff u(base+4) < na_frac. Synchronises the stream.
 void launch_synth(double* A, int64_t n, int64_t m, int k, int64_t col0, uint64_t base, double noise, double na_frac,
                   cudaStream_t st);
+// the block rows [row0, row0+nr) x columns [col0, col0+mc) of the global n_global x (any) matrix, written with leading dimension nr
+void launch_synth_block(double* A, int64_t n_global, int64_t row0, int64_t nr, int64_t col0, int64_t mc, int k, uint64_t base,
+                        double noise, double na_frac, cudaStream_t st);
 
 // ---- gram.cu: K1/K1r/K6 of SURVEY.md §2.1 ----
 // G = Y Y' (k x k) with the reference's regularisation (src/update_with_missing.cpp:19-24). Y is k x len.
 // part must hold gram_splits(len) * k * k doubles.
 int  gram_splits(int64_t len);
 void launch_gram(const double* Y, int k, int64_t len, const double* pen /*[3] host, nullptr = raw unregularised Gram*/, double* part, double* G, cudaStream_t st);
+// G = Graw + the reference's regularisation (src/update_with_missing.cpp:20-24); used after the raw Gram was all-reduced
+void launch_gram_regularise(const double* Graw, int k, const double* pen, double* G, cudaStream_t st);
 // sumW = rowSums(Y) (src/update_with_missing.cpp:27); part must hold gram_splits(len) * k doubles
 void launch_rowsum(const double* Y, int k, int64_t len, double* part, double* out, cudaStream_t st);
 
@@ -71,8 +76,10 @@ void launch_cross_tc(const CrossPlan& plan, const __half* a_hi, const __half* a_
                      const double* unscale, const double* center, const double* fsum, double* Qp, cudaStream_t st);
 // means over the finite entries of the columns (ncol values) and rows (len values, nullptr to skip) of A
 void launch_means(const double* A, int64_t len, int64_t ncol, double* colmean, double* rowmean, cudaStream_t st);
-// sA[0] = power-of-two scale of A from max |A| (scratch: one u64)
-void launch_absmax_scale(const double* A, int64_t total, unsigned long long* scratch, double* sA, cudaStream_t st);
+// maxbits[0] = bit pattern of max |A| over the finite entries (a u64: non-negative doubles order like integers, so shards
+// combine with an integer max); sA[0] = the power-of-two scale derived from it
+void launch_absmax(const double* A, int64_t total, unsigned long long* maxbits, cudaStream_t st);
+void launch_scale_from_max(const unsigned long long* maxbits, double* sA, cudaStream_t st);
 // A (len x ncol col-major fp64) -> planes of A (pitch ld_a) and of A' (pitch ld_t; pass nullptr to skip)
 void launch_split_matrix(const double* A, int64_t len, int64_t ncol, const double* sA, const double* colmean,
                          const double* rowmean, __half* a_hi, __half* a_lo, int64_t ld_a,
@@ -90,8 +97,9 @@ void launch_solve_ls(int method, double* X, const double* G, const double* Qp, i
 
 // ---- solve_scd_tpc.cu: K3/K4 thread-per-column SCD (method 1, dense A, k <= 64): same contract as launch_solve_ls ----
 bool scd_tpc_supported(int k);
+size_t scd_tpc_scratch_doubles();
 void launch_scd_tpc(double* X, const double* G, const double* Qp, int splits, const uint8_t* mask, int k, int64_t ncol,
-                    double l1, unsigned max_iter, double rel_tol, unsigned long long* sweeps, cudaStream_t st);
+                    double l1, unsigned max_iter, double rel_tol, unsigned long long* sweeps, double* scratch, cudaStream_t st);
 
 // ---- solve_ls_missing.cu: K9 + K4/K5, the NA path of the square loss (src/update_with_missing.cpp:58-117) ----
 // Y k x len (the fixed factor), A len x ncol (non-finite = missing), Gfull the raw (unregularised) Gram of Y,

@@ -156,9 +156,10 @@ void launch_kb(double* X, const double* G, const double* Qp, int splits, const u
 }  // namespace
 
 bool scd_tpc_supported(int k) { return k >= 1 && k <= 64; }
+size_t scd_tpc_scratch_doubles() { return 2; }
 
 void launch_scd_tpc(double* X, const double* G, const double* Qp, int splits, const uint8_t* mask, int k, int64_t ncol,
-                    double l1, unsigned max_iter, double rel_tol, unsigned long long* sweeps, cudaStream_t st)
+                    double l1, unsigned max_iter, double rel_tol, unsigned long long* sweeps, double* /*scratch*/, cudaStream_t st)
 {
     NNLM_REQUIRE(scd_tpc_supported(k), "thread-per-column SCD supports rank k <= 64");
     if (ncol <= 0) return;

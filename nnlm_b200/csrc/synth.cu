@@ -28,6 +28,35 @@ __global__ void k_uniform(double* __restrict__ out, int64_t count, uint64_t seed
 }
 
 // one thread per element, i fastest (coalesced stores of A and loads of Wtrue)
+// general block: rows [row0, row0+nr) of the n_global-row matrix; Wt holds the nr local rows (leading dimension nr)
+__global__ void __launch_bounds__(256)
+k_synth_block(double* __restrict__ A, const double* __restrict__ Wt, const double* __restrict__ Ht, int64_t n_global,
+              int64_t row0, int64_t nr, int k, int64_t col0, uint64_t base, double noise, double na_frac)
+{
+    extern __shared__ double hs[];
+    const int64_t j = blockIdx.y;
+    for (int c = threadIdx.x; c < k; c += blockDim.x) hs[c] = Ht[c + (int64_t)k * j];
+    __syncthreads();
+    const double nanv = __longlong_as_double(0x7ff8000000000000ll);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nr; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int c = 0; c < k; c++) s = fma(Wt[i + nr * c], hs[c], s);
+        const uint64_t idx = (uint64_t)(row0 + i) + (uint64_t)n_global * (uint64_t)(col0 + j);
+        s = fma(noise, splitmix_u(base + 3, idx), s);
+        if (na_frac > 0.0 && splitmix_u(base + 4, idx) < na_frac) s = nanv;
+        A[i + nr * j] = s;
+    }
+}
+
+__global__ void k_uniform_rows(double* __restrict__ out, int64_t n_global, int64_t row0, int64_t nr, int k, uint64_t seed)
+{
+    const int64_t total = nr * k;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e % nr, c = e / nr;
+        out[e] = splitmix_u(seed, (uint64_t)(row0 + i) + (uint64_t)n_global * (uint64_t)c);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_synth(double* __restrict__ A, const double* __restrict__ Wt, const double* __restrict__ Ht, int64_t n, int64_t m,
         int k, int64_t col0, uint64_t base, double noise, double na_frac)
@@ -73,6 +102,24 @@ void launch_synth(double* A, int64_t n, int64_t m, int k, int64_t col0, uint64_t
         NNLM_LAUNCHED();
     }
     NNLM_CUDA_CHECK(cudaStreamSynchronize(st));    // Wt/Ht are freed on return
+}
+
+void launch_synth_block(double* A, int64_t n_global, int64_t row0, int64_t nr, int64_t col0, int64_t mc, int k, uint64_t base,
+                        double noise, double na_frac, cudaStream_t st)
+{
+    if (nr <= 0 || mc <= 0) return;
+    DevBuf<double> Wt((size_t)nr * k), Ht((size_t)k * mc);
+    k_uniform_rows<<<(int)std::min<int64_t>(ceil_div(nr * k, 256), 148 * 8), 256, 0, st>>>(Wt.p, n_global, row0, nr, k, base + 1);
+    NNLM_LAUNCHED();
+    launch_uniform(Ht.p, (int64_t)k * mc, base + 2, (uint64_t)k * (uint64_t)col0, 1.0, st);
+    for (int64_t j0 = 0; j0 < mc; j0 += 65535) {
+        const int64_t cnt = std::min<int64_t>(65535, mc - j0);
+        dim3 grid((unsigned)std::min<int64_t>(ceil_div(nr, 256), 64), (unsigned)cnt);
+        k_synth_block<<<grid, 256, sizeof(double) * k, st>>>(A + nr * j0, Wt.p, Ht.p + (int64_t)k * j0, n_global, row0, nr, k,
+                                                            col0 + j0, base, noise, na_frac);
+        NNLM_LAUNCHED();
+    }
+    NNLM_CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
 }  // namespace nnlm

@@ -28,6 +28,17 @@ def synth_init(n, m, k, seed_base=0):
     return W0, H0
 
 
+def synth_block(n_global, row0, nr, col0, mc, k, seed_base=0, noise=0.1, na_frac=0.0):
+    """Rows [row0, row0+nr) x columns [col0, col0+mc) of the synthetic matrix, generated on the device (nnlm_synth_block)."""
+    A = np.empty((nr, mc), dtype=np.float64, order="F")
+    err = C.create_string_buffer(512)
+    rc = K.lib().nnlm_synth_block(K.d(A), C.c_int64(n_global), C.c_int64(row0), C.c_int64(nr), C.c_int64(col0), C.c_int64(mc),
+                                  C.c_int32(k), C.c_uint64(seed_base), C.c_double(noise), C.c_double(na_frac), err,
+                                  C.c_size_t(512))
+    K.check(rc, err)
+    return A
+
+
 def synth_matrix(n, m, k, col0=0, seed_base=0, noise=0.1, na_frac=0.0):
     """The synthetic A of BASELINE.md §4, generated on the device and copied to the host (nnlm_synth_matrix)."""
     A = np.empty((n, m), dtype=np.float64, order="F")
@@ -40,13 +51,19 @@ def synth_matrix(n, m, k, col0=0, seed_base=0, noise=0.1, na_frac=0.0):
 
 class Session:
     def __init__(self, A=None, k=1, method=1, alpha=(0, 0, 0), beta=(0, 0, 0), inner_max_iter=50, inner_rel_tol=1e-9,
-                 Wm=None, Hm=None, precision=K.PREC_AUTO, device=-1, synthetic=None, timing=False):
+                 Wm=None, Hm=None, precision=K.PREC_AUTO, device=-1, synthetic=None, timing=False, comm=None, shards=None,
+                 shape=None):
         """A: host matrix (n x m), or synthetic=dict(n=, m=, seed_base=0, noise=0.1, na_frac=0.0, col_offset=0)."""
         self._h = C.c_void_p()
         self.k = int(k)
         a = K.vec3(alpha); b = K.vec3(beta)
         opt = K.Options(); opt.precision = int(precision); opt.device = int(device); opt.verbose_timing = int(bool(timing))
         err = C.create_string_buffer(512)
+        self._comm = comm              # keep the communicator alive as long as the session
+        if comm is not None:
+            opt.comm = comm.handle
+            if synthetic is None and shards is None:
+                raise ValueError("a sharded session needs synthetic=... or shards=(Acol, Arow) with shape=(n, m)")
         if synthetic is not None:
             self.n, self.m = int(synthetic["n"]), int(synthetic["m"])
             opt.col_offset = int(synthetic.get("col_offset", 0))
@@ -55,6 +72,15 @@ class Session:
                 C.c_uint64(int(synthetic.get("seed_base", 0))), C.c_double(synthetic.get("noise", 0.1)),
                 C.c_double(synthetic.get("na_frac", 0.0)), K.d(a), K.d(b), C.c_uint32(int(inner_max_iter)),
                 C.c_double(inner_rel_tol), C.c_int32(method), C.byref(opt), err, C.c_size_t(512))
+        elif shards is not None:
+            # host shards of this rank: Acol = A[:, c0:c0+mc] (n x mc), Arow = A[r0:r0+nr, :] (nr x m)
+            Acol = K.f64(shards[0], copy=False); Arow = K.f64(shards[1], copy=False)
+            self.n, self.m = int(shape[0]), int(shape[1])
+            wm = K.lgl(Wm); hm = K.lgl(Hm)
+            rc = K.lib().nnlm_session_create_sharded(
+                C.byref(self._h), K.d(Acol), K.d(Arow), C.c_int64(self.n), C.c_int64(self.m), C.c_int32(self.k), K.i32(wm),
+                K.i32(hm), K.d(a), K.d(b), C.c_uint32(int(inner_max_iter)), C.c_double(inner_rel_tol), C.c_int32(method),
+                C.byref(opt), err, C.c_size_t(512))
         else:
             A = K.f64(A, copy=False)
             self.n, self.m = A.shape
