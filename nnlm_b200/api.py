@@ -160,11 +160,15 @@ def nnmf(A, k=1, alpha=(0.0, 0.0, 0.0), beta=(0.0, 0.0, 0.0), method="scd", loss
     Kt = im["K"]
     alpha = K.vec3(alpha)
     beta = K.vec3(beta)
-    min_k = min(n, m)                                                               # R/nnmf.R:157-166
-    isna = np.isnan(A)
-    if isna.any():
-        min_k = min(min_k, int((m - isna.sum(axis=1)).min()), int((n - isna.sum(axis=0)).min()))
-    del isna
+    if check_k and np.all(alpha == 0) and np.all(beta == 0):                        # R/nnmf.R:157-166
+        min_k = min(n, m)
+        if Kt > min_k or np.isnan(A).any():
+            isna = np.isnan(A)
+            if isna.any():
+                min_k = min(min_k, int((m - isna.sum(axis=1)).min()), int((n - isna.sum(axis=0)).min()))
+            del isna
+    else:
+        min_k = Kt
     if check_k and Kt > min_k and np.all(alpha == 0) and np.all(beta == 0):
         raise ValueError(f"k larger than {min_k} is not recommended, unless properly masked or regularized.\n"
                          "Set check.k = FALSE if you want to skip this checking.")

@@ -1,0 +1,19 @@
+// scd_dmma_ct1.cu — instantiations of the blocked DMMA SCD solver (scd_dmma.cuh) for 8-column tiles, padded rank 8*nb
+#include "scd_dmma.cuh"
+
+namespace nnlm { namespace scd_dmma {
+void launch_ct1(int nb, NNLM_SCD_ARGS)
+{
+    switch (nb) {
+        case 1: launch<1, 1>(NNLM_SCD_PASS); break;
+        case 2: launch<2, 1>(NNLM_SCD_PASS); break;
+        case 3: launch<3, 1>(NNLM_SCD_PASS); break;
+        case 4: launch<4, 1>(NNLM_SCD_PASS); break;
+        case 5: launch<5, 1>(NNLM_SCD_PASS); break;
+        case 6: launch<6, 1>(NNLM_SCD_PASS); break;
+        case 7: launch<7, 1>(NNLM_SCD_PASS); break;
+        case 8: launch<8, 1>(NNLM_SCD_PASS); break;
+        default: throw Error(NNLM_E_ARG, "scd_dmma: rank k > 64 is not instantiated");
+    }
+}
+} }
