@@ -1,0 +1,25 @@
+/* Minimal stand-in for R's headers: just enough declarations to type-check r/src/shim.c where R is absent. NOT R. */
+#ifndef MOCK_RINTERNALS_H
+#define MOCK_RINTERNALS_H
+#include <stddef.h>
+typedef struct SEXPREC* SEXP;
+typedef ptrdiff_t R_xlen_t;
+typedef int Rboolean;
+#define FALSE 0
+#define TRUE 1
+#define REALSXP 14
+#define VECSXP 19
+#define STRSXP 16
+extern SEXP R_NilValue, R_NamesSymbol;
+int Rf_nrows(SEXP); int Rf_ncols(SEXP); int Rf_asInteger(SEXP); double Rf_asReal(SEXP); int Rf_asLogical(SEXP);
+R_xlen_t XLENGTH(SEXP); double* REAL(SEXP); int* LOGICAL(SEXP);
+SEXP Rf_allocMatrix(int, int, int); SEXP Rf_allocVector(int, R_xlen_t); SEXP Rf_xlengthgets(SEXP, R_xlen_t);
+SEXP Rf_ScalarReal(double); SEXP Rf_ScalarInteger(int); SEXP Rf_mkChar(const char*);
+SEXP Rf_setAttrib(SEXP, SEXP, SEXP); SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP); void SET_STRING_ELT(SEXP, R_xlen_t, SEXP);
+SEXP Rf_protect(SEXP); void Rf_unprotect(int);
+#define PROTECT(x) Rf_protect(x)
+#define UNPROTECT(n) Rf_unprotect(n)
+void Rf_error(const char*, ...); void Rf_warning(const char*, ...); void Rf_onintr(void);
+void R_CheckUserInterrupt(void); Rboolean R_ToplevelExec(void (*)(void*), void*);
+void GetRNGstate(void); void PutRNGstate(void); double unif_rand(void);
+#endif
