@@ -17,7 +17,7 @@
 //
 // Mapping (UMMA D[M x N] = A[M x K] * B[N x K]^T, both operands K-major, SWIZZLE_128B):
 //   M = 128 columns j of A   (operand rows = columns of the matrix, contiguous along the contraction index i)
-//   N = NP  = k padded to 32/64   (rows a of the factor, row-major copy made by split_factor)
+//   N = NP  = k padded to 32/64/128 (rows a of the factor, row-major copy made by split_factor)
 //   K = 64 fp16 (= one 128-byte swizzle row) per pipeline stage, UMMA_K = 16 -> 4 k-steps x 3 products per stage
 // Work = (tile, k-block) units in tile-major order, cut into gridDim.x equal contiguous ranges (stream-K): every CTA
 // streams the same number of bytes; a tile shared by several CTAs receives one fp64 partial per CTA in slot order
@@ -256,17 +256,23 @@ k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ 
                 const uint32_t buf = chunk & 1, tph = (chunk >> 1) & 1;
                 mbar_wait(&tfull[buf], tph);
                 tc_fence_after();
-                uint32_t r0[CPT], r1[CPT];
+                constexpr int CH = CPT > 32 ? 32 : CPT;          // TMEM columns read per tcgen05.ld
                 const uint32_t t0 = tmem_base + lane_addr + buf * (2 * NP) + half * CPT;
-                TmemLd<CPT>::ld(t0, r0);
-                TmemLd<CPT>::ld(t0 + NP, r1);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[buf]);       // buffer may be overwritten by the next-but-one chunk
 #pragma unroll
-                for (int c = 0; c < CPT; c++)
-                    acc[c] += (double)__uint_as_float(r0[c]) + (double)__uint_as_float(r1[c]) * LO_UNSCALE;
+                for (int ch = 0; ch < CPT / CH; ch++) {
+                    uint32_t r0[CH], r1[CH];
+                    TmemLd<CH>::ld(t0 + ch * CH, r0);
+                    TmemLd<CH>::ld(t0 + NP + ch * CH, r1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (ch == CPT / CH - 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[buf]);   // buffer may be overwritten by the next-but-one chunk
+                    }
+#pragma unroll
+                    for (int c = 0; c < CH; c++)
+                        acc[ch * CH + c] += (double)__uint_as_float(r0[c]) + (double)__uint_as_float(r1[c]) * LO_UNSCALE;
+                }
                 u = chunk_end;
                 chunk++;
             }
@@ -523,8 +529,8 @@ void launch_np(const CrossPlan& plan, const __half* a_hi, const __half* a_lo, co
 
 }  // namespace
 
-bool cross_tc_supported(int k) { return k >= 1 && k <= 64; }
-int cross_tc_np(int k) { return k <= 32 ? 32 : 64; }
+bool cross_tc_supported(int k) { return k >= 1 && k <= 128; }
+int cross_tc_np(int k) { return k <= 32 ? 32 : (k <= 64 ? 64 : 128); }
 int64_t cross_tc_ld(int64_t len) { return (len + 7) / 8 * 8; }     // TMA row pitch must be a multiple of 16 bytes
 
 CrossPlan cross_tc_plan(int k, int64_t len, int64_t ncol)
@@ -552,9 +558,10 @@ CrossPlan cross_tc_plan(int k, int64_t len, int64_t ncol)
 void launch_cross_tc(const CrossPlan& plan, const __half* a_hi, const __half* a_lo, const __half* f_hi, const __half* f_lo,
                      const double* unscale, const double* center, const double* fsum, double* Qp, cudaStream_t st)
 {
-    NNLM_REQUIRE(cross_tc_supported(plan.k), "tensor-core cross-product supports rank k <= 64");
-    if (plan.np == 32) launch_np<32, 5>(plan, a_hi, a_lo, f_hi, f_lo, unscale, center, fsum, Qp, st);
-    else               launch_np<64, 4>(plan, a_hi, a_lo, f_hi, f_lo, unscale, center, fsum, Qp, st);
+    NNLM_REQUIRE(cross_tc_supported(plan.k), "tensor-core cross-product supports rank k <= 128");
+    if (plan.np == 32)      launch_np<32, 5>(plan, a_hi, a_lo, f_hi, f_lo, unscale, center, fsum, Qp, st);
+    else if (plan.np == 64) launch_np<64, 4>(plan, a_hi, a_lo, f_hi, f_lo, unscale, center, fsum, Qp, st);
+    else                    launch_np<128, 3>(plan, a_hi, a_lo, f_hi, f_lo, unscale, center, fsum, Qp, st);
 }
 
 void launch_means(const double* A, int64_t len, int64_t ncol, double* colmean, double* rowmean, cudaStream_t st)
@@ -600,9 +607,11 @@ void launch_split_factor(const double* F, int k, int64_t len, int64_t ld, int np
     const int64_t total = (int64_t)k * len;
     k_rowmax<<<(int)std::min<int64_t>(ceil_div(total, 256 * 8), 148 * 4), 256, sizeof(unsigned long long) * k, st>>>(F, k, len, rowmax);
     NNLM_LAUNCHED();
-    k_make_scales<<<1, 128, 0, st>>>(rowmax, k, np, sA, scales, unscale);
+    k_make_scales<<<1, 128, 0, st>>>(rowmax, k, np, sA, scales, unscale);     // np <= 128
     NNLM_LAUNCHED();
-    k_split_factor<<<(unsigned)ceil_div(ld, 64), 256, sizeof(double) * 64 * (k + 1), st>>>(F, k, len, ld, np, scales, hi, lo);
+    const size_t smem = sizeof(double) * 64 * (k + 1);
+    if (smem > 48 * 1024) NNLM_CUDA_CHECK(cudaFuncSetAttribute(k_split_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_split_factor<<<(unsigned)ceil_div(ld, 64), 256, smem, st>>>(F, k, len, ld, np, scales, hi, lo);
     NNLM_LAUNCHED();
 }
 

@@ -32,7 +32,7 @@ namespace nnlm {
 namespace scd_dmma {
 
 // resident warps per CTA (one CTA per SM): narrower tiles hold fewer accumulators per thread
-template <int CT> struct Cfg { static constexpr int WARPS = (CT == 4) ? 8 : 12; };
+template <int NB, int CT> struct Cfg { static constexpr int WARPS = (NB > 8) ? 8 : ((CT == 4) ? 8 : 12); };
 
 // D(8x8) += A(8x4, row-major) * B(4x8, col-major): a = A[lane>>2][lane&3], b = B[lane&3][lane>>2], c = C[lane>>2][2*(lane&3) + {0,1}]
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
@@ -53,12 +53,12 @@ __device__ __forceinline__ double and_mask(double x, int m)
 }
 
 template <int NB, int CT>   // NB blocks of 8 coordinates (padded rank KB = 8*NB), CT column tiles of 8 (NC = 8*CT columns per warp)
-__global__ void __launch_bounds__(32 * Cfg<CT>::WARPS, 1)
+__global__ void __launch_bounds__(32 * Cfg<NB, CT>::WARPS, 1)
 k_scd_dmma(double* __restrict__ X, const double* __restrict__ G, const double* __restrict__ Qp, int splits,
            const uint8_t* __restrict__ mask, int k, int64_t ncol, double l1, unsigned max_iter, double rel_tol,
            unsigned long long* __restrict__ sweeps, unsigned int* __restrict__ next_group)
 {
-    constexpr int KB = 8 * NB, NC = 8 * CT, KS = KB + 4, WARPS = Cfg<CT>::WARPS;
+    constexpr int KB = 8 * NB, NC = 8 * CT, KS = KB + 4, WARPS = Cfg<NB, CT>::WARPS;
     extern __shared__ __align__(16) double sm[];
     double* gc = sm;                                   // [KB][KS]: gc[c*KS + r] = V[r, c] (symmetric; zero padded)
     double* rinv = gc + KB * KS;                       // [KB] 1 / V[c,c] (0 for padding)
@@ -108,15 +108,23 @@ k_scd_dmma(double* __restrict__ X, const double* __restrict__ G, const double* _
                     mu[rt][ct][e] = (r < k && c < cnt) ? l1 - q : 0.0;
                 }
         // ---- per-column state of the sequential part (lane = column) ----
-        unsigned long long mbits = 0;
+        constexpr int MW = (KB + 63) / 64;                           // 64-bit words of the per-column coordinate mask
+        unsigned long long mbits[MW];
         const bool have = lane < cnt;
-        if (mask != nullptr && have) {
-            const uint8_t* mc = mask + (col0 + lane) * k;
-            for (int r = 0; r < k; r++) mbits |= (unsigned long long)(mc[r] != 0) << r;
+        bool any_free = false;
+#pragma unroll
+        for (int w = 0; w < MW; w++) {
+            mbits[w] = 0;
+            if (mask != nullptr && have) {
+                const uint8_t* mc = mask + (col0 + lane) * k;
+                for (int r = 64 * w; r < k && r < 64 * w + 64; r++) mbits[w] |= (unsigned long long)(mc[r] != 0) << (r - 64 * w);
+            }
+            const int kw = k - 64 * w;                               // coordinates of this word that exist
+            const unsigned long long kmask = kw >= 64 ? ~0ull : (kw <= 0 ? 0ull : ((1ull << kw) - 1ull));
+            any_free = any_free || (mbits[w] & kmask) != kmask;
+            mbits[w] |= ~kmask;                                      // padding coordinates are never updated
         }
-        const unsigned long long kmask = (k >= 64) ? ~0ull : ((1ull << k) - 1ull);
-        mbits |= ~kmask;                                             // padding coordinates are never updated
-        bool cont = have && (mbits & kmask) != kmask;                // fully masked column: src/update_with_missing.cpp:33-34
+        bool cont = have && any_free;                                // fully masked column: src/update_with_missing.cpp:33-34
         __syncwarp();
 
         // ---- mu += V h : the same block update with D := h, including the diagonal tile ----
@@ -147,7 +155,9 @@ k_scd_dmma(double* __restrict__ X, const double* __restrict__ G, const double* _
         int cur = 0;                                                 // dsm buffer of the block being processed
         for (unsigned it = 0; it < max_iter; it++) {
             if (!__any_sync(0xffffffffu, cont)) break;
-            const unsigned long long fz = cont ? mbits : ~0ull;      // coordinates this sweep must leave alone
+            unsigned long long fz[MW];                                // coordinates this sweep must leave alone
+#pragma unroll
+            for (int w = 0; w < MW; w++) fz[w] = cont ? mbits[w] : ~0ull;
             bool flag = false;
 #pragma unroll
             for (int b = 0; b < NB; b++) {
@@ -178,7 +188,7 @@ k_scd_dmma(double* __restrict__ X, const double* __restrict__ G, const double* _
                     const int cc = 8 * b + c;
                     const double hc = h8[c];
                     const double cand = clamp0(fma(-m8[c], rinv[cc], hc));
-                    const int live = ((fz >> cc) & 1ull) ? 0 : -1;
+                    const int live = ((fz[cc >> 6] >> (cc & 63)) & 1ull) ? 0 : -1;
                     const double d = and_mask(cand - hc, live);
                     dd[c] = d;
                     h8[c] = live ? cand : hc;
@@ -249,7 +259,7 @@ template <int NB, int CT>
 void launch(double* X, const double* G, const double* Qp, int splits, const uint8_t* mask, int k, int64_t ncol, double l1,
             unsigned max_iter, double rel_tol, unsigned long long* sweeps, unsigned int* counter, cudaStream_t st)
 {
-    constexpr int KB = 8 * NB, NC = 8 * CT, KS = KB + 4, WARPS = Cfg<CT>::WARPS;
+    constexpr int KB = 8 * NB, NC = 8 * CT, KS = KB + 4, WARPS = Cfg<NB, CT>::WARPS;
     const size_t smem = sizeof(double) * ((size_t)KB * KS + KB + (size_t)WARPS * (KB * NC + 24 * NC));
     auto kern = k_scd_dmma<NB, CT>;
     NNLM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -264,10 +274,12 @@ void launch(double* X, const double* G, const double* Qp, int splits, const uint
     double l1, unsigned max_iter, double rel_tol, unsigned long long* sweeps, unsigned int* counter, cudaStream_t st
 #define NNLM_SCD_PASS X, G, Qp, splits, mask, k, ncol, l1, max_iter, rel_tol, sweeps, counter, st
 
-// explicit-instantiation entry points (one translation unit per tile width keeps the build parallel); nb = ceil(k / 8) <= 8
-void launch_ct4(int nb, NNLM_SCD_ARGS);   // 32-column tiles
-void launch_ct2(int nb, NNLM_SCD_ARGS);   // 16-column tiles
-void launch_ct1(int nb, NNLM_SCD_ARGS);   //  8-column tiles
+// explicit-instantiation entry points (several translation units keep the build parallel); nb = ceil(k / 8)
+void launch_ct4(int nb, NNLM_SCD_ARGS);      // 32-column tiles, nb <= 8
+void launch_ct2(int nb, NNLM_SCD_ARGS);      // 16-column tiles, nb <= 8
+void launch_ct1(int nb, NNLM_SCD_ARGS);      //  8-column tiles, nb <= 8
+void launch_ct1_big_a(int nb, NNLM_SCD_ARGS);  //  8-column tiles, 9 <= nb <= 12
+void launch_ct1_big_b(int nb, NNLM_SCD_ARGS);  //  8-column tiles, 13 <= nb <= 16 (k <= 128)
 
 }  // namespace scd_dmma
 }  // namespace nnlm

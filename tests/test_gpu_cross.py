@@ -9,7 +9,8 @@ from conftest import umat
 
 pytestmark = pytest.mark.gpu
 
-SHAPES = [(7, 100, 50), (50, 1000, 300), (50, 1003, 257), (64, 4099, 130), (33, 20000, 1000), (3, 64, 128), (1, 10, 3)]
+SHAPES = [(7, 100, 50), (50, 1000, 300), (50, 1003, 257), (64, 4099, 130), (33, 20000, 1000), (3, 64, 128), (1, 10, 3),
+          (100, 3001, 200), (128, 2048, 256), (65, 777, 129)]
 
 
 def inputs(k, n, m, signed=False):

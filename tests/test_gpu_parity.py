@@ -172,7 +172,7 @@ def test_nnmf_fast_precision_parity(method, inner, T):
     np.testing.assert_allclose(got.target_loss, ref["target_loss"], rtol=1e-5)
 
 
-@pytest.mark.parametrize("k", [20, 50, 64])
+@pytest.mark.parametrize("k", [20, 50, 64, 65, 100, 128])
 def test_update_fast_precision_larger_k(k):
     n, m = 3000, 500
     Wt = umat(1, k, n); A = synth(n, m, k, seed=30); H0 = umat(3, k, m)
