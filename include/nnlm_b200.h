@@ -89,6 +89,9 @@ typedef struct nnlm_stats {
     uint64_t solve_launches;
     double comm_ms;           /* device time in the NCCL collectives (sharded path)                */
     uint64_t comm_bytes;      /* bytes this rank received through them                             */
+    double host_setup_ms;     /* host wall clock: allocation + upload + ingest + factor/mask set-up  */
+    double host_loop_ms;      /* host wall clock of the outer loop (incl. error evaluations)        */
+    double host_finish_ms;    /* host wall clock: download of W, H                                  */
 } nnlm_stats;
 
 /* ---- c_nnmf (src/nnmf.cpp:4-220) -------------------------------------------------------------

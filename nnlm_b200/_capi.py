@@ -34,7 +34,8 @@ class Stats(C.Structure):
                 ("launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("precision_used", C.c_int32), ("reserved0", C.c_int32),
                 ("gram_ms", C.c_double), ("cross_launches", C.c_uint64), ("solve_launches", C.c_uint64),
-                ("comm_ms", C.c_double), ("comm_bytes", C.c_uint64)]
+                ("comm_ms", C.c_double), ("comm_bytes", C.c_uint64),
+                ("host_setup_ms", C.c_double), ("host_loop_ms", C.c_double), ("host_finish_ms", C.c_double)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_ if not f.startswith("reserved")}

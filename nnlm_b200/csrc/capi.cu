@@ -1,6 +1,7 @@
 // capi.cu — the C ABI of include/nnlm_b200.h: argument checking, the outer ANLS loop of c_nnmf (src/nnmf.cpp:48-220),
 // c_nnlm (src/nnlm.cpp:36-52), a single update() (src/update_with_missing.cpp), and the device-resident session used by
 // the benchmark. All arithmetic happens in the kernels driven by Engine; this file is bookkeeping.
+#include <chrono>
 #include <cmath>
 #include <memory>
 #include <vector>
@@ -141,6 +142,10 @@ int nnlm_nnmf(const double* A, int64_t n, int64_t m, int32_t K,
         if (stats) std::memset(stats, 0, sizeof *stats);
         const uint64_t launches0 = launch_counter().load();
         Events ev;
+        auto now = [] { return std::chrono::steady_clock::now(); };
+        auto ms_since = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::milli>(b - a).count(); };
+        const auto h0 = now();
 
         Engine eng(n, m, K, method, precision_of(opt, n, m), opt ? opt->device : -1);
         eng.timer.enable(opt && opt->verbose_timing);
@@ -152,6 +157,8 @@ int nnlm_nnmf(const double* A, int64_t n, int64_t m, int32_t K,
         eng.set_penalties(alpha, beta);
         eng.set_inner(inner_max_iter, inner_rel_tol);
         cudaEventRecord(ev.e[1], st);
+        eng.sync();
+        const auto h1 = now();
 
         const double N = (double)((int64_t)n * m - eng.n_missing());   // N_non_missing, :51,68
         const double mkl_const = eng.kl_const_sum() / N;               // :70-73
@@ -199,9 +206,12 @@ int nnlm_nnmf(const double* A, int64_t n, int64_t m, int32_t K,
             std::printf("%10s | %10s | %10s | %10s | %10s\n\n", "Iteration", "MSE", "MKL", "Target", "Rel. Err.");
         }
         cudaEventRecord(ev.e[2], st);
+        eng.sync();
+        const auto h2 = now();
         eng.get_factors(W, H);                                                               // :211-213
         cudaEventRecord(ev.e[3], st);
         eng.sync();
+        const auto h3 = now();
 
         if (n_err) *n_err = i_e;                                                             // :200-206
         if (n_iter) *n_iter = i;                                                             // :218
@@ -211,6 +221,9 @@ int nnlm_nnmf(const double* A, int64_t n, int64_t m, int32_t K,
             stats->upload_ms = elapsed(ev.e[0], ev.e[1]);
             stats->loop_ms = elapsed(ev.e[1], ev.e[2]);
             stats->download_ms = elapsed(ev.e[2], ev.e[3]);
+            stats->host_setup_ms = ms_since(h0, h1);
+            stats->host_loop_ms = ms_since(h1, h2);
+            stats->host_finish_ms = ms_since(h2, h3);
         }
         return NNLM_OK;
     });

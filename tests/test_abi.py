@@ -36,7 +36,7 @@ def test_abi_version_matches_header():
 
 def test_struct_layouts_match_header():
     assert C.sizeof(K.Options) == 40
-    assert C.sizeof(K.Stats) == 6 * 8 + 3 * 8 + 2 * 4 + 3 * 8 + 2 * 8
+    assert C.sizeof(K.Stats) == 6 * 8 + 3 * 8 + 2 * 4 + 3 * 8 + 2 * 8 + 3 * 8
 
 
 def test_no_cpu_fallback():
