@@ -63,12 +63,18 @@ k_gram_partial(const double* __restrict__ Y, int k, int64_t len, int64_t per_spl
 
 // Fixed-order sum of the split partials + the reference's regularisation:
 //   diag += beta0 - beta1 (if they differ); all += beta1 (if non-zero); diag += TINY_NUM   (:20-24)
-__global__ void k_gram_finish(const double* __restrict__ part, int splits, int k, double b0, double b1, int raw, double* __restrict__ G)
+// One warp per Gram element: lanes take the split partials in a strided, fixed order and a butterfly combines them
+// (bit-reproducible; the first version walked all splits in one thread and cost 59 us per half-iteration).
+__global__ void __launch_bounds__(256)
+k_gram_finish(const double* __restrict__ part, int splits, int k, double b0, double b1, int raw, double* __restrict__ G)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (e >= k * k) return;
     double s = 0.0;
-    for (int sp = 0; sp < splits; sp++) s += part[(int64_t)sp * k * k + e];
+    for (int sp = lane; sp < splits; sp += 32) s += part[(int64_t)sp * k * k + e];
+    s = warp_sum(s);
+    if (lane != 0) return;
     const bool diag = (e / k) == (e % k);
     if (raw) { G[e] = s; return; }
     if (b0 != b1 && diag) s += b0 - b1;
@@ -100,11 +106,13 @@ k_rowsum_partial(const double* __restrict__ Y, int k, int64_t len, int64_t per_s
 
 __global__ void k_rowsum_finish(const double* __restrict__ part, int splits, int k, double* __restrict__ out)
 {
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // one warp per row
     if (a >= k) return;
     double s = 0.0;
-    for (int sp = 0; sp < splits; sp++) s += part[(int64_t)sp * k + a];
-    out[a] = s;
+    for (int sp = lane; sp < splits; sp += 32) s += part[(int64_t)sp * k + a];
+    s = warp_sum(s);
+    if (lane == 0) out[a] = s;
 }
 
 }  // namespace
@@ -131,7 +139,7 @@ void launch_gram(const double* Y, int k, int64_t len, const double* pen, double*
         k_gram_partial<8><<<dim3(splits, nb, nb), 256, 0, st>>>(Y, k, len, per_split, part);
     }
     NNLM_LAUNCHED();
-    k_gram_finish<<<(k * k + 255) / 256, 256, 0, st>>>(part, splits, k, pen ? pen[0] : 0.0, pen ? pen[1] : 0.0, pen ? 0 : 1, G);
+    k_gram_finish<<<(k * k + 7) / 8, 256, 0, st>>>(part, splits, k, pen ? pen[0] : 0.0, pen ? pen[1] : 0.0, pen ? 0 : 1, G);
     NNLM_LAUNCHED();
 }
 
@@ -160,7 +168,7 @@ void launch_rowsum(const double* Y, int k, int64_t len, double* part, double* ou
     const int64_t per_split = ceil_div(len, splits);
     k_rowsum_partial<<<splits, 256, 256 * sizeof(double), st>>>(Y, k, len, per_split, part);
     NNLM_LAUNCHED();
-    k_rowsum_finish<<<(k + 255) / 256, 256, 0, st>>>(part, splits, k, out);
+    k_rowsum_finish<<<(k + 7) / 8, 256, 0, st>>>(part, splits, k, out);
     NNLM_LAUNCHED();
 }
 
