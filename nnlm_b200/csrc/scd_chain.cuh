@@ -100,8 +100,10 @@ k_scd_chain(double* __restrict__ X, const double* __restrict__ G, const double* 
                 for (int e = 0; e < 2; e++) {
                     const int r = 8 * rt + gid, c = 8 * ct + 2 * tig + e;
                     double q = 0.0;
-                    if (r < k && c < cnt)
+                    if (r < k && c < cnt) {
+#pragma unroll 1
                         for (int sp = 0; sp < splits; sp++) q += Qp[((int64_t)sp * ncol + col0 + c) * k + r];
+                    }
                     mu[rt][ct][e] = (r < k && c < cnt) ? l1 - q : 0.0;
                 }
         // ---- per-column state of the sequential part (lane = column) ----
@@ -114,6 +116,7 @@ k_scd_chain(double* __restrict__ X, const double* __restrict__ G, const double* 
             mbits[w] = 0;
             if (mask != nullptr && have) {
                 const uint8_t* mc = mask + (col0 + lane) * k;
+#pragma unroll 1
                 for (int r = 64 * w; r < k && r < 64 * w + 64; r++) mbits[w] |= (unsigned long long)(mc[r] != 0) << (r - 64 * w);
             }
             const int kw = k - 64 * w;                               // coordinates of this word that exist
@@ -124,20 +127,17 @@ k_scd_chain(double* __restrict__ X, const double* __restrict__ G, const double* 
         bool cont = have && any_free;                                // fully masked column: src/update_with_missing.cpp:33-34
         __syncwarp();
 
-        // ---- mu += V h : the block update with D := h ----
+        // ---- mu += V h : the block update with D := h (a rolled loop over the half-blocks: it runs once per group) ----
+#pragma unroll 1
+        for (int hb = 0; hb < NH; hb++) {
+            double bf[CT];
 #pragma unroll
-        for (int b = 0; b < NB; b++) {
+            for (int ct = 0; ct < CT; ct++) bf[ct] = hs[(4 * hb + tig) * NC + 8 * ct + gid];
 #pragma unroll
-            for (int kh = 0; kh < 2; kh++) {
-                double bf[CT];
+            for (int rt = 0; rt < NB; rt++) {
+                const double a = gc[(4 * hb + tig) * KS + 8 * rt + gid];
 #pragma unroll
-                for (int ct = 0; ct < CT; ct++) bf[ct] = hs[(8 * b + 4 * kh + tig) * NC + 8 * ct + gid];
-#pragma unroll
-                for (int rt = 0; rt < NB; rt++) {
-                    const double a = gc[(8 * b + 4 * kh + tig) * KS + 8 * rt + gid];
-#pragma unroll
-                    for (int ct = 0; ct < CT; ct++) dmma(mu[rt][ct][0], mu[rt][ct][1], a, bf[ct]);
-                }
+                for (int ct = 0; ct < CT; ct++) dmma(mu[rt][ct][0], mu[rt][ct][1], a, bf[ct]);
             }
         }
         // the first diagonal tile, one thread per column
@@ -176,7 +176,7 @@ k_scd_chain(double* __restrict__ X, const double* __restrict__ G, const double* 
                 // (2) the sequential steps + the deferred MMAs of block pb. The convergence test (3 fp64 operations per step)
                 // is only evaluated while some running column of the tile has not exceeded the tolerance yet in this sweep.
                 const double* wb = wl + b * 32;
-                const bool need_flag = __any_sync(0xffffffffu, cont && flagbits >= 0);
+                const bool need_flag = NB > 8 || __any_sync(0xffffffffu, cont && flagbits >= 0);
                 auto steps = [&](auto with_flag) {
 #pragma unroll
                     for (int c = 0; c < 8; c++) {
@@ -196,20 +196,23 @@ k_scd_chain(double* __restrict__ X, const double* __restrict__ G, const double* 
                         // 2|d| > tol (hn + hc + 1e-16)  <=>  (tol/2)(hn + hc) + (tol/2)1e-16 - |d| < 0 : collect the sign bits
                         if (decltype(with_flag)::value) flagbits |= __double2hiint(fma(hn + hc, tolh, c0 - fabs(d)));
                         if (NB > 1) {
-                            int slot = 0;                                // deferred (kh, rt) pairs are dealt round-robin to the steps
+                            // deferred (rt, kh) pairs are dealt round-robin to the steps: pair (rt, kh) goes to step
+                            // (its ordinal among the pairs with rt != b) mod 8 — a pure function of the unrolled indices
 #pragma unroll
                             for (int rt = 0; rt < NB; rt++)
 #pragma unroll
-                                for (int kh = 0; kh < 2; kh++)
-                                    if (rt != b && 2 * pb + kh < NH && (slot++ & 7) == c) {
+                                for (int kh = 0; kh < 2; kh++) {
+                                    const int ord = 2 * rt + kh - (rt > b ? 2 : 0);
+                                    if (rt != b && 2 * pb + kh < NH && (ord & 7) == c) {
                                         const double a = gc[(8 * pb + 4 * kh + tig) * KS + 8 * rt + gid];
 #pragma unroll
                                         for (int ct = 0; ct < CT; ct++) dmma(mu[rt][ct][0], mu[rt][ct][1], a, bfp[kh][ct]);
                                     }
+                                }
                         }
                     }
                 };
-                if (need_flag) steps(std::true_type{}); else steps(std::false_type{});
+                if (NB > 8 || need_flag) steps(std::true_type{}); else steps(std::false_type{});   // (one copy keeps big ranks unrollable)
                 // (3) publish d and the new h
                 if (lane < NC) {
 #pragma unroll
@@ -272,13 +275,17 @@ void launch(double* X, const double* G, const double* Qp, int splits, const uint
     double l1, unsigned max_iter, double rel_tol, unsigned long long* sweeps, unsigned int* counter, cudaStream_t st
 #define NNLM_SCDC_PASS X, G, Qp, splits, mask, k, ncol, l1, max_iter, rel_tol, sweeps, counter, st
 
-// explicit-instantiation entry points (several translation units keep the build parallel); nh = ceil(k / 4) <= 16
+// explicit-instantiation entry points (several translation units keep the build parallel); nh = ceil(k / 4) <= 32
 void launch_ct4_lo(int nh, NNLM_SCDC_ARGS);   // 32-column tiles, nh 1..8
 void launch_ct4_hi(int nh, NNLM_SCDC_ARGS);   // 32-column tiles, nh 9..16
 void launch_ct2_lo(int nh, NNLM_SCDC_ARGS);   // 16-column tiles
 void launch_ct2_hi(int nh, NNLM_SCDC_ARGS);
 void launch_ct1_lo(int nh, NNLM_SCDC_ARGS);   //  8-column tiles
 void launch_ct1_hi(int nh, NNLM_SCDC_ARGS);
+void launch_big_a(int nh, NNLM_SCDC_ARGS);    //  8-column tiles, 8 warps, nh 17..20 (k 65..80)
+void launch_big_b(int nh, NNLM_SCDC_ARGS);    //  nh 21..24
+void launch_big_c(int nh, NNLM_SCDC_ARGS);    //  nh 25..28
+void launch_big_d(int nh, NNLM_SCDC_ARGS);    //  nh 29..32 (k <= 128)
 
 }  // namespace scd_chain
 }  // namespace nnlm

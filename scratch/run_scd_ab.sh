@@ -1,6 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 180 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 || exit 1
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
 show() { python - "$1" "$2" <<'PY'
 import json,sys
@@ -11,12 +10,5 @@ except Exception as e:
     print(sys.argv[2], "failed", e); print(open(sys.argv[1].replace(".json",".err")).read()[-1500:])
 PY
 }
-for cfg in "2 0" "2 2" "2 4"; do
-  set -- $cfg
-  NNLM_SCD_IMPL=$1 NNLM_SCD_CT=$2 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu --no-e2e > gpurun_out/ab_$1_$2.json 2> gpurun_out/ab_$1_$2.err
-  show gpurun_out/ab_$1_$2.json "impl=$1 ct=$2"
-done
-for c in 3 4; do
-  NNLM_SCD_IMPL=2 timeout 600 python bench.py --config $c --steps 3 --warmup 3 --no-cpu --no-e2e > gpurun_out/cfg$c.json 2> gpurun_out/cfg$c.err
-  show gpurun_out/cfg$c.json "config $c"
-done
+timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu --no-e2e > gpurun_out/c2.json 2> gpurun_out/c2.err; show gpurun_out/c2.json "config 2"
+timeout 600 python bench.py --config 5 --steps 5 --warmup 3 --no-cpu --no-e2e > gpurun_out/c5.json 2> gpurun_out/c5.err; show gpurun_out/c5.json "config 5 (1 GPU)"

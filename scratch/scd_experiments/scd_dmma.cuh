@@ -275,9 +275,6 @@ void launch(double* X, const double* G, const double* Qp, int splits, const uint
 #define NNLM_SCD_PASS X, G, Qp, splits, mask, k, ncol, l1, max_iter, rel_tol, sweeps, counter, st
 
 // explicit-instantiation entry points (several translation units keep the build parallel); nb = ceil(k / 8)
-void launch_ct4(int nb, NNLM_SCD_ARGS);      // 32-column tiles, nb <= 8
-void launch_ct2(int nb, NNLM_SCD_ARGS);      // 16-column tiles, nb <= 8
-void launch_ct1(int nb, NNLM_SCD_ARGS);      //  8-column tiles, nb <= 8
 void launch_ct1_big_a(int nb, NNLM_SCD_ARGS);  //  8-column tiles, 9 <= nb <= 12
 void launch_ct1_big_b(int nb, NNLM_SCD_ARGS);  //  8-column tiles, 13 <= nb <= 16 (k <= 128)
 
