@@ -70,7 +70,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -241,10 +241,11 @@ def main():
     algo_bytes = float(n) * m * s_bytes / world + 8.0 * k * (n + m)
     achieved = algo_bytes / (cross_ms * 1e-3) / 1e9 if cross_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": 2.08e9 if (world == 1 and not args.small) else None,
+                "traffic": 2.10e9 if (world == 1 and not args.small and args.config == 2) else None,
                 "kernel": "k_cross_tc (cross-product: one pass over A per half-iteration), per GPU",
                 "algorithmic_bytes_per_launch": algo_bytes, "ms_per_launch": cross_ms, "peak_source": peak_src,
-                "traffic_source": "ncu --set full dram__bytes_read+write per launch, profiles/r1_b_*.md" if world == 1 else None,
+                "traffic_source": ("ncu --set full dram__bytes_read+write per launch (W-half 2.05e9, H-half 2.15e9), "
+                                  "profiles/r1_n_final_build.md") if (world == 1 and not args.small and args.config == 2) else None,
                 "share_of_step": {"cross": st["cross_ms"] / dev_ms, "solve": st["solve_ms"] / dev_ms,
                                   "gram": st["gram_ms"] / dev_ms, "comm": st["comm_ms"] / dev_ms}}
     launches = int(sum_over_ranks(float(st["launches"])))

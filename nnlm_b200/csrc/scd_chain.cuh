@@ -6,7 +6,8 @@
 // ran at ~250 cycles per step because every step waited on shared-memory broadcasts of V, a second dependent chain (the
 // short-circuit convergence test) shared the in-order issue slot, and the chain's DFMAs queued behind other warps' DMMAs.
 // Here:
-//   * the chain never touches mu. At block entry P_r = h_r - mu_r / V_rr (the unclamped candidates) are formed for the 8
+//   * the chain never touches mu. At block entry P_r = h_r - mu_r / V_rr (the unclamped candidates; the division is a
+//     multiplication done on the fragments before the tile is transposed) are formed for the 8
 //     coordinates; step c reads cand = P_c, derives d_c, and folds it into the later candidates with ONE fma per row,
 //     P_r -= (V_rc / V_rr) d_c  (r > c, multipliers precomputed per half-iteration). Dependent path per step:
 //     DFMA -> {sign test || DADD} -> select -> select(mask) instead of DFMA -> clamp -> DADD -> mask -> DFMA;
@@ -41,6 +42,7 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 
 __device__ __forceinline__ double flip_sign(double x) { return __hiloint2double(__double2hiint(x) ^ 0x80000000, __double2loint(x)); }
 
+__host__ __device__ constexpr int widx(int c, int r) { return c * (15 - c) / 2 + (r - c - 1); }   // dense index of the pair (c, r > c)
 // offset of step c's multipliers inside a block's 32-entry record (7-c used entries, padded to an even count)
 __host__ __device__ constexpr int woff(int c) { return c == 0 ? 0 : c == 1 ? 8 : c == 2 ? 14 : c == 3 ? 20 : c == 4 ? 24 : c == 5 ? 28 : 30; }
 
@@ -140,10 +142,21 @@ k_scd_chain(double* __restrict__ X, const double* __restrict__ G, const double* 
                 for (int ct = 0; ct < CT; ct++) dmma(mu[rt][ct][0], mu[rt][ct][1], a, bf[ct]);
             }
         }
-        // the first diagonal tile, one thread per column
+        // the first diagonal tile scaled by 1 / V_rr (row gid of the fragment), one thread per column
+        {
+            const double ri = rinv[gid];
 #pragma unroll
-        for (int ct = 0; ct < CT; ct++)
-            *reinterpret_cast<double2*>(tsm + gid * NC + 8 * ct + 2 * tig) = make_double2(mu[0][ct][0], mu[0][ct][1]);
+            for (int ct = 0; ct < CT; ct++)
+                *reinterpret_cast<double2*>(tsm + gid * NC + 8 * ct + 2 * tig) = make_double2(mu[0][ct][0] * ri, mu[0][ct][1] * ri);
+        }
+        // multipliers of the first PRE steps of the next block, fetched while the MMAs of step (4) run (narrow tiles have the
+        // registers for it): the chain then starts without waiting on shared-memory broadcasts
+        constexpr int PRE = (NB > 8) ? 0 : (CT == 1 ? 7 : (CT == 2 ? 3 : 0));
+        double wn[PRE ? widx(PRE, PRE + 1) : 1];
+#pragma unroll
+        for (int c = 0; c < PRE; c++)
+#pragma unroll
+            for (int r = c + 1; r < 8; r++) wn[widx(c, r)] = wl[woff(c) + (r - c - 1)];
 
         // ---- sweeps ----
         // Software pipeline per block b:  (1) candidates of the block;  (2) the 8 sequential steps, interleaved with the
@@ -171,7 +184,7 @@ k_scd_chain(double* __restrict__ X, const double* __restrict__ G, const double* 
 #pragma unroll
                 for (int r = 0; r < 8; r++) {
                     h8[r] = hs[(8 * b + r) * NC + colx];
-                    P[r] = fma(-tsm[r * NC + colx], rinv[8 * b + r], h8[r]);
+                    P[r] = h8[r] - tsm[r * NC + colx];
                 }
                 // (2) the sequential steps + the deferred MMAs of block pb. The convergence test (3 fp64 operations per step)
                 // is only evaluated while some running column of the tile has not exceeded the tolerance yet in this sweep.
@@ -192,7 +205,7 @@ k_scd_chain(double* __restrict__ X, const double* __restrict__ G, const double* 
                         dd[c] = d;
                         h8[c] = hn;
 #pragma unroll
-                        for (int r = c + 1; r < 8; r++) P[r] = fma(-wb[woff(c) + (r - c - 1)], d, P[r]);
+                        for (int r = c + 1; r < 8; r++) P[r] = fma(-(c < PRE ? wn[widx(c, r)] : wb[woff(c) + (r - c - 1)]), d, P[r]);
                         // 2|d| > tol (hn + hc + 1e-16)  <=>  (tol/2)(hn + hc) + (tol/2)1e-16 - |d| < 0 : collect the sign bits
                         if (decltype(with_flag)::value) flagbits |= __double2hiint(fma(hn + hc, tolh, c0 - fabs(d)));
                         if (NB > 1) {
@@ -235,9 +248,16 @@ k_scd_chain(double* __restrict__ X, const double* __restrict__ G, const double* 
                         for (int ct = 0; ct < CT; ct++) dmma(mu[nb][ct][0], mu[nb][ct][1], a, bfp[kh][ct]);
                     }
                 }
+                {
+                    const double ri = rinv[8 * nb + gid];
 #pragma unroll
-                for (int ct = 0; ct < CT; ct++)
-                    *reinterpret_cast<double2*>(tsm + gid * NC + 8 * ct + 2 * tig) = make_double2(mu[nb][ct][0], mu[nb][ct][1]);
+                    for (int ct = 0; ct < CT; ct++)
+                        *reinterpret_cast<double2*>(tsm + gid * NC + 8 * ct + 2 * tig) = make_double2(mu[nb][ct][0] * ri, mu[nb][ct][1] * ri);
+                }
+#pragma unroll
+                for (int c = 0; c < PRE; c++)
+#pragma unroll
+                    for (int r = c + 1; r < 8; r++) wn[widx(c, r)] = wl[nb * 32 + woff(c) + (r - c - 1)];
             }
             if (cont) t++;
             cont = cont && (flagbits < 0 || (0.0 > rel_tol));
