@@ -46,30 +46,82 @@ __device__ __forceinline__ unsigned warp_solve_ls(double (&h)[RPL], const double
 #pragma unroll
         for (int s = 0; s < RPL; s++) { mu[s] -= q[s]; if (l1 != 0.0) mu[s] += l1; }
 
-        for (; t < max_iter && cont; t++) {
+        // Sweeps. Per step the dependent path is: owner lane forms cand = max(0, h_c - mu_c / V_cc) and d (a multiplication
+        // with the reciprocal taken once per column; clamp on the bit pattern) -> ONE broadcast of d -> one FMA per owned row.
+        // d = 0 stands for the reference's `tmp != Hj(k)` test (adding 0 * V leaves mu bit-identical), so the step has no
+        // data-dependent branch; the exit test is evaluated by the owner lane only and combined once per sweep.
+        // (A first version broadcast h_c and mu_c, divided on every lane and branched on the result: ~550 cycles per step.)
+        double rinv[RPL];
+#pragma unroll
+        for (int s = 0; s < RPL; s++) {
+            const int r = lane + 32 * s;
+            rinv[s] = (r < k) ? 1.0 / gs[r + KR * r] : 0.0;
+        }
+        bool anymask = false;
+#pragma unroll
+        for (int s = 0; s < RPL; s++) anymask = anymask || mk[s] != 0u;
+        if (!anymask) {
+            // unmasked column (the common case): no per-step branches at all. The Gram column of step c+1 is fetched
+            // during step c; the owner lane's h and its exit test are selects / sign bits, not divergent code.
+            const double tolh = 0.5 * rel_tol, c0 = tolh * TINY_NUM;
+            for (; t < max_iter && cont; t++) {
+                int flagi = 0;
+#pragma unroll
+                for (int sc = 0; sc < RPL; sc++) {
+                    const int cnt = min(32, k - 32 * sc);
+                    double gn[RPL];
+#pragma unroll
+                    for (int s = 0; s < RPL; s++) gn[s] = gs[lane + 32 * s + KR * min(32 * sc, k - 1)];
+                    for (int lc = 0; lc < cnt; lc++) {
+                        const int c = 32 * sc + lc;
+                        double g[RPL];
+#pragma unroll
+                        for (int s = 0; s < RPL; s++) g[s] = gn[s];
+                        const int cn = (lc + 1 < cnt) ? c + 1 : c;
+#pragma unroll
+                        for (int s = 0; s < RPL; s++) gn[s] = gs[lane + 32 * s + KR * cn];
+                        const double hc = h[sc];
+                        double cand = fma(-mu[sc], rinv[sc], hc);
+                        const int keep = ~(__double2hiint(cand) >> 31);                       // max(cand, +0) on the bit pattern
+                        cand = __hiloint2double(__double2hiint(cand) & keep, __double2loint(cand) & keep);
+                        const double down = cand - hc;
+                        const double d = shfl_d(down, lc);
+#pragma unroll
+                        for (int s = 0; s < RPL; s++) mu[s] = fma(d, g[s], mu[s]);
+                        const bool own = lane == lc;
+                        h[sc] = own ? cand : hc;
+                        // 2|d| > tol (new + old + 1e-16)  <=>  (tol/2)(new + old) + (tol/2)1e-16 - |d| < 0
+                        const int over = __double2hiint(fma(cand + hc, tolh, c0 - fabs(down)));
+                        flagi |= own ? over : 0;
+                    }
+                }
+                cont = __any_sync(0xffffffffu, flagi < 0) || (0.0 > rel_tol);
+            }
+        }
+        for (; anymask && t < max_iter && cont; t++) {
             bool flag = false;
 #pragma unroll
             for (int sc = 0; sc < RPL; sc++) {
+#pragma unroll 4
                 for (int lc = 0; lc < 32; lc++) {
                     const int c = 32 * sc + lc;
                     if (c >= k) break;
                     if ((mk[sc] >> lc) & 1u) continue;
-                    const double hc = shfl_d(h[sc], lc);
-                    const double muc = shfl_d(mu[sc], lc);
-                    double cand = hc - muc / gs[c + KR * c];
-                    if (cand < 0) cand = 0;
-                    if (cand != hc) {
-                        const double d = cand - hc;
+                    const double hc = h[sc];
+                    double cand = fma(-mu[sc], rinv[sc], hc);
+                    cand = __hiloint2double(__double2hiint(cand) & ~(__double2hiint(cand) >> 31),
+                                            __double2loint(cand) & ~(__double2hiint(cand) >> 31));      // max(cand, +0)
+                    const double down = cand - hc;
+                    const double d = shfl_d(down, lc);
 #pragma unroll
-                        for (int s = 0; s < RPL; s++) mu[s] = fma(d, gs[lane + 32 * s + KR * c], mu[s]);
-                        const double num = 2 * fabs(hc - cand), den = cand + hc + TINY_NUM;
-                        const bool over = (den > 0) ? (num > rel_tol * den) : (num / den > rel_tol);
-                        flag = flag || over;
-                        if (lane == lc) h[sc] = cand;
+                    for (int s = 0; s < RPL; s++) mu[s] = fma(d, gs[lane + 32 * s + KR * c], mu[s]);
+                    if (lane == lc) {
+                        h[sc] = cand;
+                        flag = flag || (2 * fabs(down) > rel_tol * (cand + hc + TINY_NUM));
                     }
                 }
             }
-            cont = flag || (0.0 > rel_tol);
+            cont = __any_sync(0xffffffffu, flag) || (0.0 > rel_tol);
         }
     } else {
         for (; t < max_iter && cont; t++) {

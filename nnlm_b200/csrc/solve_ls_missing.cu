@@ -8,7 +8,11 @@
 //   complement  G_j = G_full - sum_{i missing} y_i y_i'      (G_full = unregularised Gram of the whole factor)
 //   direct      G_j =          sum_{i present} y_i y_i'
 // The index set is compacted in ascending order (ballot + prefix), so the summation order is fixed. Rows y_i are staged
-// 32 at a time; every thread keeps a 4x4 register tile of the Gram. Warp 0 then runs warp_solve_ls on the finished Gram.
+// 64 at a time in shared memory and the symmetric rank-64 update runs as fp64 tensor-core MMAs (DMMA.8x8x4, the full
+// fp64 rate with two 8-byte operands per thread): only the 8x8 tiles on and below the diagonal are accumulated
+// (nt(nt+1)/2 of them, nt = ceil(k/8), dealt round-robin to the 8 warps as C fragments) and mirrored when the Gram is
+// written out. A first version with 4x4 DFMA register tiles fed by LDS.128 ran the per-column Gram at ~1/4 of the fp64
+// rate over the full square (config 4: 268 ms per ANLS iteration). Warp 0 then runs warp_solve_ls on the finished Gram.
 // "Missing" is bit-exactly the reference's predicate: the entry is not finite (find_finite, :80-83), evaluated on the
 // stored value of A (fp64, or fp32 whose non-finite set is identical by construction of the conversion).
 #include <algorithm>
@@ -21,7 +25,12 @@ namespace nnlm {
 namespace {
 
 constexpr int NT = 256;
-constexpr int CH = 32;     // staged rows per step
+constexpr int CH = 64;     // staged rows per step
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
 template <typename TA> __device__ __forceinline__ bool missing_v(TA v);
 template <> __device__ __forceinline__ bool missing_v<double>(double v) { return is_missing(v); }
@@ -35,15 +44,26 @@ k_solve_ls_missing(double* __restrict__ X, const double* __restrict__ Y, const T
                    unsigned max_iter, double rel_tol, unsigned long long* __restrict__ sweeps)
 {
     constexpr int KR = 32 * RPL;
-    constexpr int KT = KR / 4;                 // 4x4 tiles per dimension
-    constexpr int TPT = (KT * KT + NT - 1) / NT;   // tiles per thread
+    constexpr int KP = KR + 4;                 // pitch of the staged rows: A/B fragment loads hit 32 distinct banks
+    constexpr int NTMAX = KR / 8;              // 8x8 tiles per dimension
+    constexpr int TPW = (NTMAX * (NTMAX + 1) / 2 + NT / 32 - 1) / (NT / 32);   // lower-triangle tiles per warp
     extern __shared__ __align__(32) double smd[];
     double* gs = smd;                          // [KR][KR] (column-major, leading dimension KR)
-    double* ys = gs + KR * KR;                 // [CH][KR] staged rows
+    double* ys = gs + KR * KR;                 // [CH][KP] staged rows
     __shared__ int64_t s_idx[CH];
     __shared__ int s_wcnt[NT / 32];
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
+    // the tiles of this warp: tile t of the lower triangle is (ta, tb) with t = ta (ta + 1) / 2 + tb, tb <= ta
+    const int ntk = (k + 7) / 8, ntiles = ntk * (ntk + 1) / 2;
+    int ta_[TPW], tb_[TPW];
+#pragma unroll
+    for (int j = 0; j < TPW; j++) {
+        const int t = warp + (NT / 32) * j;
+        int ta = 0;
+        while ((ta + 1) * (ta + 2) / 2 <= t) ta++;
+        ta_[j] = ta; tb_[j] = t - ta * (ta + 1) / 2;
+    }
 
     for (int64_t col = blockIdx.x; col < ncol; col += gridDim.x) {
         const TA* Aj = A + len * col;
@@ -67,37 +87,26 @@ k_solve_ls_missing(double* __restrict__ X, const double* __restrict__ Y, const T
         const bool complement = 2 * n_missing <= len;        // subtract the missing rows, or add the present ones
         const double sgn = complement ? -1.0 : 1.0;
 
-        // ---- accumulate the 4x4 tiles ----
-        double acc[TPT][4][4];
+        // ---- accumulate the lower-triangle 8x8 tiles as DMMA C fragments ----
+        double acc[TPW][2];
 #pragma unroll
-        for (int t = 0; t < TPT; t++)
-#pragma unroll
-            for (int u = 0; u < 4; u++)
-#pragma unroll
-                for (int v = 0; v < 4; v++) acc[t][u][v] = 0.0;
+        for (int j = 0; j < TPW; j++) acc[j][0] = acc[j][1] = 0.0;
 
         __syncthreads();
         auto flush = [&](int fill) {
-            // stage rows y_i for the collected indices, then rank-`fill` update of every tile
+            // stage rows y_i for the collected indices (zero beyond `fill` and beyond k), then the rank-`fill` update
             for (int e = threadIdx.x; e < CH * KR; e += NT) {
                 const int s = e / KR, r = e % KR;
-                ys[e] = (s < fill && r < k) ? Y[r + (int64_t)k * s_idx[s]] : 0.0;
+                ys[s * KP + r] = (s < fill && r < k) ? Y[r + (int64_t)k * s_idx[s]] : 0.0;
             }
             __syncthreads();
+            const int steps = (fill + 3) >> 2;
+            for (int q = 0; q < steps; q++) {
+                const double* row = ys + (4 * q + tig) * KP + gid;
 #pragma unroll
-            for (int t = 0; t < TPT; t++) {
-                const int tile = threadIdx.x + t * NT;
-                if (tile < KT * KT) {
-                    const int ta = tile % KT, tb = tile / KT;
-                    for (int s = 0; s < fill; s++) {
-                        const double4 ya = *reinterpret_cast<const double4*>(ys + s * KR + 4 * ta);
-                        const double4 yb = *reinterpret_cast<const double4*>(ys + s * KR + 4 * tb);
-                        const double a4[4] = {ya.x, ya.y, ya.z, ya.w}, b4[4] = {yb.x, yb.y, yb.z, yb.w};
-#pragma unroll
-                        for (int u = 0; u < 4; u++)
-#pragma unroll
-                            for (int v = 0; v < 4; v++) acc[t][u][v] = fma(a4[u], b4[v], acc[t][u][v]);
-                    }
+                for (int j = 0; j < TPW; j++) {
+                    if (warp + (NT / 32) * j < ntiles)
+                        dmma(acc[j][0], acc[j][1], row[8 * ta_[j]], row[8 * tb_[j]]);
                 }
             }
             __syncthreads();
@@ -130,25 +139,24 @@ k_solve_ls_missing(double* __restrict__ X, const double* __restrict__ Y, const T
 
         // ---- G_j = (complement ? G_full : 0) + sgn * acc, then the reference's regularisation (:98-103) ----
         __syncthreads();
+        for (int e = threadIdx.x; e < KR * KR; e += NT) gs[e] = 0.0;      // rows / columns >= 8 * ntk stay zero
+        __syncthreads();
 #pragma unroll
-        for (int t = 0; t < TPT; t++) {
-            const int tile = threadIdx.x + t * NT;
-            if (tile < KT * KT) {
-                const int ta = tile % KT, tb = tile / KT;
+        for (int j = 0; j < TPW; j++) {
+            if (warp + (NT / 32) * j < ntiles) {
 #pragma unroll
-                for (int u = 0; u < 4; u++)
-#pragma unroll
-                    for (int v = 0; v < 4; v++) {
-                        const int a = 4 * ta + u, b = 4 * tb + v;
-                        double g = 0.0;
-                        if (a < k && b < k) {
-                            g = (complement ? Gfull[a + k * b] : 0.0) + sgn * acc[t][u][v];
-                            if (p0 != p1 && a == b) g += p0 - p1;
-                            if (p1 != 0.0) g += p1;
-                            if (a == b) g += TINY_NUM;
-                        }
-                        gs[a + KR * b] = g;
+                for (int e = 0; e < 2; e++) {
+                    const int a = 8 * ta_[j] + gid, b = 8 * tb_[j] + 2 * tig + e;      // C fragment: row gid, columns 2 tig + e
+                    double g = 0.0;
+                    if (a < k && b < k) {
+                        g = (complement ? Gfull[a + k * b] : 0.0) + sgn * acc[j][e];
+                        if (p0 != p1 && a == b) g += p0 - p1;
+                        if (p1 != 0.0) g += p1;
+                        if (a == b) g += TINY_NUM;
                     }
+                    if (ta_[j] != tb_[j] || a >= b) gs[a + KR * b] = g;           // diagonal tiles: keep their lower half ...
+                    if (ta_[j] != tb_[j] || a > b) gs[b + KR * a] = g;            // ... and mirror it (the Gram is symmetric)
+                }
             }
         }
         __syncthreads();
@@ -187,7 +195,7 @@ void launch_rpl(int method, double* X, const double* Y, const TA* A, const doubl
                 unsigned long long* sweeps, cudaStream_t st)
 {
     constexpr int KR = 32 * RPL;
-    const size_t smem = sizeof(double) * ((size_t)KR * KR + (size_t)CH * KR);
+    const size_t smem = sizeof(double) * ((size_t)KR * KR + (size_t)CH * (KR + 4));
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ncol, 148 * 8));
     if (method == 1) {
         auto kern = k_solve_ls_missing<RPL, 1, TA>;
