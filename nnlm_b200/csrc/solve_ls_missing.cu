@@ -4,7 +4,7 @@
 // regularises it (:98-103) and runs the same coordinate solver (:107-117). The masked cross-product Wt[:,nm_j]*A[nm_j,j]
 // (:91) is the ordinary cross-product of A with its non-finite entries read as zero and comes from the cross kernels.
 //
-// One CTA per column. The per-column Gram is built in shared memory, in fp64, from whichever index set is smaller:
+// One CTA per column. The per-column Gram is built in fp64 from whichever index set is smaller:
 //   complement  G_j = G_full - sum_{i missing} y_i y_i'      (G_full = unregularised Gram of the whole factor)
 //   direct      G_j =          sum_{i present} y_i y_i'
 // The index set is compacted in ascending order (ballot + prefix), so the summation order is fixed. Rows y_i are staged
@@ -12,7 +12,9 @@
 // fp64 rate with two 8-byte operands per thread): only the 8x8 tiles on and below the diagonal are accumulated
 // (nt(nt+1)/2 of them, nt = ceil(k/8), dealt round-robin to the 8 warps as C fragments) and mirrored when the Gram is
 // written out. A first version with 4x4 DFMA register tiles fed by LDS.128 ran the per-column Gram at ~1/4 of the fp64
-// rate over the full square (config 4: 268 ms per ANLS iteration). Warp 0 then runs warp_solve_ls on the finished Gram.
+// rate over the full square, and solved each column on warp 0 while the other seven warps of the CTA waited (config 4: 268 ms
+// per ANLS iteration). The work is now two kernels: A builds the Grams with all warps and writes them to a scratch
+// buffer (k*k doubles per column, chunked to ~1 GB), B solves one column per warp, 7 warps per CTA.
 // "Missing" is bit-exactly the reference's predicate: the entry is not finite (find_finite, :80-83), evaluated on the
 // stored value of A (fp64, or fp32 whose non-finite set is identical by construction of the conversion).
 #include <algorithm>
@@ -36,20 +38,19 @@ template <typename TA> __device__ __forceinline__ bool missing_v(TA v);
 template <> __device__ __forceinline__ bool missing_v<double>(double v) { return is_missing(v); }
 template <> __device__ __forceinline__ bool missing_v<float>(float v) { return ((__float_as_uint(v) >> 23) & 0xffu) == 0xffu; }
 
-template <int RPL, int METHOD, typename TA>
+// Kernel A: the regularised per-column Grams of columns [col0, col0 + ncol) -> Gout[j][k*k] (column-major k x k each).
+template <int RPL, typename TA>
 __global__ void __launch_bounds__(NT)
-k_solve_ls_missing(double* __restrict__ X, const double* __restrict__ Y, const TA* __restrict__ A,
-                   const double* __restrict__ Gfull, const double* __restrict__ Qp, int splits,
-                   const uint8_t* __restrict__ mask, int k, int64_t len, int64_t ncol, double p0, double p1, double l1,
-                   unsigned max_iter, double rel_tol, unsigned long long* __restrict__ sweeps)
+k_gram_missing(const double* __restrict__ Y, const TA* __restrict__ A, const double* __restrict__ Gfull,
+               const uint8_t* __restrict__ mask, int k, int64_t len, int64_t col0, int64_t ncol, double p0, double p1,
+               double* __restrict__ Gout)
 {
     constexpr int KR = 32 * RPL;
     constexpr int KP = KR + 4;                 // pitch of the staged rows: A/B fragment loads hit 32 distinct banks
     constexpr int NTMAX = KR / 8;              // 8x8 tiles per dimension
     constexpr int TPW = (NTMAX * (NTMAX + 1) / 2 + NT / 32 - 1) / (NT / 32);   // lower-triangle tiles per warp
     extern __shared__ __align__(32) double smd[];
-    double* gs = smd;                          // [KR][KR] (column-major, leading dimension KR)
-    double* ys = gs + KR * KR;                 // [CH][KP] staged rows
+    double* ys = smd;                          // [CH][KP] staged rows
     __shared__ int64_t s_idx[CH];
     __shared__ int s_wcnt[NT / 32];
 
@@ -65,7 +66,8 @@ k_solve_ls_missing(double* __restrict__ X, const double* __restrict__ Y, const T
         ta_[j] = ta; tb_[j] = t - ta * (ta + 1) / 2;
     }
 
-    for (int64_t col = blockIdx.x; col < ncol; col += gridDim.x) {
+    for (int64_t cl = blockIdx.x; cl < ncol; cl += gridDim.x) {
+        const int64_t col = col0 + cl;
         const TA* Aj = A + len * col;
         const uint8_t* mcol = mask ? mask + (int64_t)k * col : nullptr;
         if (mcol) {                                          // src/update_with_missing.cpp:77-78
@@ -95,9 +97,19 @@ k_solve_ls_missing(double* __restrict__ X, const double* __restrict__ Y, const T
         __syncthreads();
         auto flush = [&](int fill) {
             // stage rows y_i for the collected indices (zero beyond `fill` and beyond k), then the rank-`fill` update
-            for (int e = threadIdx.x; e < CH * KR; e += NT) {
-                const int s = e / KR, r = e % KR;
-                ys[s * KP + r] = (s < fill && r < k) ? Y[r + (int64_t)k * s_idx[s]] : 0.0;
+            // (all loads of a thread are issued before its first store: a rolled load -> store loop paid the L2 latency
+            //  sixteen times per flush and was 28 % of the kernel's samples)
+            constexpr int PER = CH * KR / NT;
+            double v[PER];
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const int e = threadIdx.x + i * NT, s = e / KR, r = e % KR;
+                v[i] = (s < fill && r < k) ? Y[r + (int64_t)k * s_idx[s]] : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < PER; i++) {
+                const int e = threadIdx.x + i * NT;
+                ys[(e / KR) * KP + (e % KR)] = v[i];
             }
             __syncthreads();
             const int steps = (fill + 3) >> 2;
@@ -138,55 +150,77 @@ k_solve_ls_missing(double* __restrict__ X, const double* __restrict__ Y, const T
         }
 
         // ---- G_j = (complement ? G_full : 0) + sgn * acc, then the reference's regularisation (:98-103) ----
-        __syncthreads();
-        for (int e = threadIdx.x; e < KR * KR; e += NT) gs[e] = 0.0;      // rows / columns >= 8 * ntk stay zero
-        __syncthreads();
+        double* Gj = Gout + (int64_t)k * k * cl;
 #pragma unroll
         for (int j = 0; j < TPW; j++) {
             if (warp + (NT / 32) * j < ntiles) {
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     const int a = 8 * ta_[j] + gid, b = 8 * tb_[j] + 2 * tig + e;      // C fragment: row gid, columns 2 tig + e
-                    double g = 0.0;
                     if (a < k && b < k) {
-                        g = (complement ? Gfull[a + k * b] : 0.0) + sgn * acc[j][e];
+                        double g = (complement ? Gfull[a + k * b] : 0.0) + sgn * acc[j][e];
                         if (p0 != p1 && a == b) g += p0 - p1;
                         if (p1 != 0.0) g += p1;
                         if (a == b) g += TINY_NUM;
+                        if (ta_[j] != tb_[j] || a >= b) Gj[a + k * b] = g;            // diagonal tiles: keep their lower half ...
+                        if (ta_[j] != tb_[j] || a > b) Gj[b + k * a] = g;             // ... and mirror it (the Gram is symmetric)
                     }
-                    if (ta_[j] != tb_[j] || a >= b) gs[a + KR * b] = g;           // diagonal tiles: keep their lower half ...
-                    if (ta_[j] != tb_[j] || a > b) gs[b + KR * a] = g;            // ... and mirror it (the Gram is symmetric)
                 }
             }
         }
         __syncthreads();
-
-        // ---- solve (warp 0) ----
-        if (warp == 0) {
-            double h[RPL], q[RPL];
-            unsigned mk[RPL];
-#pragma unroll
-            for (int s = 0; s < RPL; s++) {
-                const int r = lane + 32 * s;
-                const bool valid = r < k;
-                h[s] = valid ? X[r + (int64_t)k * col] : 0.0;
-                double a = 0.0;
-                if (valid)
-                    for (int sp = 0; sp < splits; sp++) a += Qp[((int64_t)sp * ncol + col) * k + r];
-                q[s] = a;
-                const bool mb = valid && mcol != nullptr && mcol[r] != 0;
-                mk[s] = __ballot_sync(0xffffffffu, mb);
-            }
-            const unsigned t = warp_solve_ls<RPL, METHOD>(h, q, mk, gs, k, l1, max_iter, rel_tol);
-#pragma unroll
-            for (int s = 0; s < RPL; s++) {
-                const int r = lane + 32 * s;
-                if (r < k) X[r + (int64_t)k * col] = h[s];
-            }
-            if (lane == 0 && t) atomicAdd(sweeps, (unsigned long long)t);
-        }
-        __syncthreads();
     }
+}
+
+// Kernel B: one WARP per column. The warp copies its column's Gram into its own slice of shared memory and runs
+// warp_solve_ls (solve_core.cuh); 7 warps per CTA at k <= 64, so 7 columns are in flight per SM instead of the one the
+// fused version had while the other seven warps of its CTA waited at a barrier (64 % of all warp samples, ncu).
+template <int RPL, int METHOD>
+__global__ void __launch_bounds__(256)
+k_solve_batch(double* __restrict__ X, const double* __restrict__ Gin, const double* __restrict__ Qp, int splits,
+              const uint8_t* __restrict__ mask, int k, int64_t col0, int64_t ncol, int64_t ncol_total, double l1,
+              unsigned max_iter, double rel_tol, unsigned long long* __restrict__ sweeps)
+{
+    constexpr int KR = 32 * RPL;
+    extern __shared__ __align__(32) double smd[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    double* gs = smd + (size_t)warp * KR * KR;      // [KR][KR] column-major, rows / columns >= k zero
+    unsigned long long my_sweeps = 0;
+    for (int e = lane; e < KR * KR; e += 32) gs[e] = 0.0;
+    for (int64_t cl = (int64_t)blockIdx.x * wpc + warp; cl < ncol; cl += (int64_t)gridDim.x * wpc) {
+        const int64_t col = col0 + cl;
+        const uint8_t* mcol = mask ? mask + (int64_t)k * col : nullptr;
+        if (mcol) {                                          // src/update_with_missing.cpp:77-78
+            int nm = 0;
+            for (int c = 0; c < k; c++) nm += mcol[c] != 0;
+            if (nm == k) continue;
+        }
+        __syncwarp();
+        const double* Gj = Gin + (int64_t)k * k * cl;
+        for (int e = lane; e < k * k; e += 32) gs[(e % k) + KR * (e / k)] = Gj[e];
+        __syncwarp();
+        double h[RPL], q[RPL];
+        unsigned mk[RPL];
+#pragma unroll
+        for (int s = 0; s < RPL; s++) {
+            const int r = lane + 32 * s;
+            const bool valid = r < k;
+            h[s] = valid ? X[r + (int64_t)k * col] : 0.0;
+            double a = 0.0;
+            if (valid)
+                for (int sp = 0; sp < splits; sp++) a += Qp[((int64_t)sp * ncol_total + col) * k + r];
+            q[s] = a;
+            const bool mb = valid && mcol != nullptr && mcol[r] != 0;
+            mk[s] = __ballot_sync(0xffffffffu, mb);
+        }
+        my_sweeps += warp_solve_ls<RPL, METHOD>(h, q, mk, gs, k, l1, max_iter, rel_tol);
+#pragma unroll
+        for (int s = 0; s < RPL; s++) {
+            const int r = lane + 32 * s;
+            if (r < k) X[r + (int64_t)k * col] = h[s];
+        }
+    }
+    if (lane == 0 && my_sweeps) atomicAdd(sweeps, my_sweeps);
 }
 
 template <int RPL, typename TA>
@@ -195,18 +229,28 @@ void launch_rpl(int method, double* X, const double* Y, const TA* A, const doubl
                 unsigned long long* sweeps, cudaStream_t st)
 {
     constexpr int KR = 32 * RPL;
-    const size_t smem = sizeof(double) * ((size_t)KR * KR + (size_t)CH * (KR + 4));
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ncol, 148 * 8));
-    if (method == 1) {
-        auto kern = k_solve_ls_missing<RPL, 1, TA>;
-        NNLM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, NT, smem, st>>>(X, Y, A, Gfull, Qp, splits, mask, k, len, ncol, pen[0], pen[1], pen[2], max_iter, rel_tol, sweeps);
-    } else {
-        auto kern = k_solve_ls_missing<RPL, 2, TA>;
-        NNLM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, NT, smem, st>>>(X, Y, A, Gfull, Qp, splits, mask, k, len, ncol, pen[0], pen[1], pen[2], max_iter, rel_tol, sweeps);
+    // per-column Grams go through a stream-ordered scratch buffer of at most ~1 GB: columns are processed in chunks
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(ncol, ((int64_t)1 << 27) / ((int64_t)k * k)));
+    double* Gout = nullptr;
+    pool_setup_once();
+    NNLM_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&Gout), sizeof(double) * (size_t)chunk * k * k, st));
+    const size_t smem_a = sizeof(double) * ((size_t)CH * (KR + 4));
+    const int wpc = std::max(1, std::min(7, (int)(220 * 1024 / (sizeof(double) * KR * KR))));   // solver warps per CTA
+    const size_t smem_b = sizeof(double) * (size_t)wpc * KR * KR;
+    auto ka = k_gram_missing<RPL, TA>;
+    NNLM_CUDA_CHECK(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+    auto kb = method == 1 ? k_solve_batch<RPL, 1> : k_solve_batch<RPL, 2>;
+    NNLM_CUDA_CHECK(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+    for (int64_t c0 = 0; c0 < ncol; c0 += chunk) {
+        const int64_t nc = std::min<int64_t>(chunk, ncol - c0);
+        const int grid_a = (int)std::max<int64_t>(1, std::min<int64_t>(nc, 148 * 8));
+        ka<<<grid_a, NT, smem_a, st>>>(Y, A, Gfull, mask, k, len, c0, nc, pen[0], pen[1], Gout);
+        NNLM_LAUNCHED();
+        const int grid_b = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(nc, wpc), 148 * 4));
+        kb<<<grid_b, 32 * wpc, smem_b, st>>>(X, Gout, Qp, splits, mask, k, c0, nc, ncol, pen[2], max_iter, rel_tol, sweeps);
+        NNLM_LAUNCHED();
     }
-    NNLM_LAUNCHED();
+    NNLM_CUDA_CHECK(cudaFreeAsync(Gout, st));
 }
 
 }  // namespace
