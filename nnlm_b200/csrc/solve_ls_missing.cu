@@ -18,6 +18,7 @@
 // "Missing" is bit-exactly the reference's predicate: the entry is not finite (find_finite, :80-83), evaluated on the
 // stored value of A (fp64, or fp32 whose non-finite set is identical by construction of the conversion).
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.cuh"
 #include "solve_core.cuh"
@@ -230,7 +231,8 @@ void launch_rpl(int method, double* X, const double* Y, const TA* A, const doubl
 {
     constexpr int KR = 32 * RPL;
     // per-column Grams go through a stream-ordered scratch buffer of at most ~1 GB: columns are processed in chunks
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(ncol, ((int64_t)1 << 27) / ((int64_t)k * k)));
+    static const int64_t budget = [] { const char* e = getenv("NNLM_NA_SCRATCH_DOUBLES"); return e ? atoll(e) : ((int64_t)1 << 27); }();
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(ncol, budget / ((int64_t)k * k)));
     double* Gout = nullptr;
     pool_setup_once();
     NNLM_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&Gout), sizeof(double) * (size_t)chunk * k * k, st));
