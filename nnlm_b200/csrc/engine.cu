@@ -72,6 +72,9 @@ Engine::Engine(int64_t n, int64_t m, int k, int method, int precision, int devic
     precision_req_ = precision;
     storage_ = (precision == NNLM_PREC_FAST) ? Storage::F32 : Storage::F64;       // refined in ingest_shards
     NNLM_CUDA_CHECK(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+    NNLM_CUDA_CHECK(cudaStreamCreateWithFlags(&st2_, cudaStreamNonBlocking));
+    NNLM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+    NNLM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
     Wt_.alloc((size_t)k_ * chunk_n_ * R);
     H_.alloc((size_t)k_ * chunk_m_ * R);
     NNLM_CUDA_CHECK(cudaMemsetAsync(Wt_.p, 0, Wt_.bytes(), st_));
@@ -81,13 +84,17 @@ Engine::Engine(int64_t n, int64_t m, int k, int method, int precision, int devic
 
 Engine::~Engine()
 {
+    if (st2_) { cudaStreamSynchronize(st2_); cudaStreamDestroy(st2_); }
     if (st_) { cudaStreamSynchronize(st_); cudaStreamDestroy(st_); }
+    if (ev_fork_) cudaEventDestroy(ev_fork_);
+    if (ev_join_) cudaEventDestroy(ev_join_);
 }
 
 void Engine::ensure_scratch()
 {
     const int64_t big = std::max(n_, m_);
     gram_part_.alloc((size_t)gram_splits(big) * k_ * k_);
+    rowsum_part_.alloc((size_t)gram_splits(big) * k_);
     G_.alloc((size_t)k_ * k_);
     Graw_.alloc((size_t)k_ * k_);
     sumY_.alloc(k_);
@@ -276,23 +283,30 @@ void Engine::set_penalties(const double* alpha, const double* beta)
 
 // The Gram of the fixed factor (src/update_with_missing.cpp:19): each rank forms the Gram of the slice it solved in the
 // previous half, the k x k partials are all-reduced (the one exchange BASELINE.json's north star names), then regularised.
-void Engine::shared_gram(const Half& h, bool raw_only)
+// It runs on the side stream, forked from the main one, and is joined right before the solver: at 8 GPUs the Gram chain
+// and its all-reduce were ~70 us of every half-iteration on the critical path.
+void Engine::fork_gram(const Half& h, bool raw_only)
 {
-    timer.begin(KernelTimer::GRAM, st_);
-    launch_gram(h.Yloc, k_, h.len_loc, nullptr, gram_part_.p, Graw_.p, st_);
-    timer.end(st_);
+    NNLM_CUDA_CHECK(cudaEventRecord(ev_fork_, st_));
+    NNLM_CUDA_CHECK(cudaStreamWaitEvent(st2_, ev_fork_, 0));
+    timer.begin(KernelTimer::GRAM, st2_);
+    launch_gram(h.Yloc, k_, h.len_loc, nullptr, gram_part_.p, Graw_.p, st2_);
+    timer.end(st2_);
     if (comm_) {
-        timer.begin(KernelTimer::COMM, st_);
-        comm_->allreduce_sum_f64(Graw_.p, (size_t)k_ * k_, st_);
+        timer.begin(KernelTimer::COMM, st2_);
+        comm_->allreduce_sum_f64(Graw_.p, (size_t)k_ * k_, st2_);
         comm_bytes += sizeof(double) * k_ * k_;
-        timer.end(st_);
+        timer.end(st2_);
     }
-    if (!raw_only) launch_gram_regularise(Graw_.p, k_, h.pen, G_.p, st_);                 // update_with_missing.cpp:20-24
+    if (!raw_only) launch_gram_regularise(Graw_.p, k_, h.pen, G_.p, st2_);                // update_with_missing.cpp:20-24
+    NNLM_CUDA_CHECK(cudaEventRecord(ev_join_, st2_));
 }
+
+void Engine::join_gram() { NNLM_CUDA_CHECK(cudaStreamWaitEvent(st_, ev_join_, 0)); }
 
 void Engine::solve_dense_ls(const Half& h, int splits)
 {
-    shared_gram(h, false);
+    join_gram();
     timer.begin(KernelTimer::SOLVE, st_);
     if (h.ncol > 0) {
         if (method_ == 1 && scd_tpc_supported(k_))
@@ -312,13 +326,14 @@ void Engine::run_half_t(const Half& h)
     const bool missing = use_missing_path();
     if (method_ <= 2) {
         const int splits = cross_simt_splits(k_, h.len, h.ncol);
+        fork_gram(h, missing);
         timer.begin(KernelTimer::CROSS, st_);
         if (h.ncol > 0) launch_cross_simt<TA>(h.Y, A, k_, h.len, h.ncol, splits, Qp_.p, st_);
         timer.end(st_);
         if (!missing) {
             solve_dense_ls(h, splits);
         } else {
-            shared_gram(h, true);
+            join_gram();
             timer.begin(KernelTimer::SOLVE, st_);
             launch_solve_ls_missing<TA>(method_, h.X, h.Y, A, Graw_.p, Qp_.p, splits, h.mask, k_, h.len, h.ncol, h.pen,
                                         inner_max_iter_, inner_rel_tol_, sweeps_.p, st_);
@@ -326,7 +341,7 @@ void Engine::run_half_t(const Half& h)
         }
     } else {
         timer.begin(KernelTimer::GRAM, st_);
-        launch_rowsum(h.Y, k_, h.len, gram_part_.p, sumY_.p, st_);                         // :27
+        launch_rowsum(h.Y, k_, h.len, rowsum_part_.p, sumY_.p, st_);                       // :27
         launch_transpose_d(h.Y, k_, h.len, Yr_.p, st_);
         timer.end(st_);
         timer.begin(KernelTimer::SOLVE, st_);
@@ -339,10 +354,11 @@ void Engine::run_half_t(const Half& h)
 void Engine::run_half_tc(const Half& h)
 {
     const CrossPlan& plan = h.w_side ? plan_w_ : plan_h_;
+    fork_gram(h, false);
     if (h.ncol > 0) {
         timer.begin(KernelTimer::GRAM, st_);
         launch_split_factor(h.Y, k_, h.len, plan.ld_f, plan.np, scale_a_.p, rowmax_.p, fscales_.p, unscale_.p, f_hi_.p, f_lo_.p, st_);
-        launch_rowsum(h.Y, k_, h.len, gram_part_.p, sumY_.p, st_);
+        launch_rowsum(h.Y, k_, h.len, rowsum_part_.p, sumY_.p, st_);
         timer.end(st_);
         timer.begin(KernelTimer::CROSS, st_);
         launch_cross_tc(plan, h.w_side ? t_hi_.p : a_hi_.p, h.w_side ? t_lo_.p : a_lo_.p, f_hi_.p, f_lo_.p, unscale_.p,
@@ -396,7 +412,7 @@ void Engine::cross_only(double* Q_host)
     int splits;
     if (storage_ == Storage::F16X2) {
         launch_split_factor(Wt_.p, k_, n_, plan_h_.ld_f, plan_h_.np, scale_a_.p, rowmax_.p, fscales_.p, unscale_.p, f_hi_.p, f_lo_.p, st_);
-        launch_rowsum(Wt_.p, k_, n_, gram_part_.p, sumY_.p, st_);
+        launch_rowsum(Wt_.p, k_, n_, rowsum_part_.p, sumY_.p, st_);
         launch_cross_tc(plan_h_, a_hi_.p, a_lo_.p, f_hi_.p, f_lo_.p, unscale_.p, colmean_.p, sumY_.p, Qp_.p, st_);
         splits = plan_h_.slots;
     } else {

@@ -122,7 +122,10 @@ private:
     void run_half(const Half& h);
     template <typename TA> void run_half_t(const Half& h);
     void run_half_tc(const Half& h);
-    void shared_gram(const Half& h, bool raw_only);     // G_ (regularised) and Graw_ from the all-reduced slice Grams
+    // G_ (regularised) and Graw_ from the all-reduced slice Grams, on the side stream: the solver is the only consumer, so
+    // the Gram kernels and their all-reduce run next to the factor split / row sums / cross-product of the main stream
+    void fork_gram(const Half& h, bool raw_only);
+    void join_gram();
     void solve_dense_ls(const Half& h, int splits);
     void gather(double* full, int64_t chunk_cols);
     void ensure_scratch();
@@ -134,7 +137,8 @@ private:
     int64_t chunk_n_, chunk_m_, r0_, nr_, c0_, mc_;
     int missing_mode_ = -1;
     Storage storage_;
-    cudaStream_t st_ = nullptr;
+    cudaStream_t st_ = nullptr, st2_ = nullptr;
+    cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
     unsigned inner_max_iter_ = 50;
     double inner_rel_tol_ = 1e-9;
     double alpha_[3] = {0, 0, 0}, beta_[3] = {0, 0, 0};
@@ -155,7 +159,7 @@ private:
     double kl_const_sum_ = 0.0;
 
     // scratch
-    DevBuf<double> gram_part_, G_, Graw_, sumY_, Qp_, Yr_, wh_, red_part_, small_, tpc_scratch_;   // small_: 16 doubles of results
+    DevBuf<double> gram_part_, rowsum_part_, G_, Graw_, sumY_, Qp_, Yr_, wh_, red_part_, small_, tpc_scratch_;   // small_: 16 doubles of results
     DevBuf<unsigned long long> sweeps_;
     PinnedBuf<double> host_small_;
 };
