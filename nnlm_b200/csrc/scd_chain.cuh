@@ -33,7 +33,13 @@ namespace scd_chain {
 
 // NH = ceil(k / 4) half-blocks of 4 coordinates (the K extent of one DMMA); NB = ceil(NH / 2) blocks of 8. A trailing half-block
 // that is all padding is skipped at compile time (k = 50: 13 half-blocks instead of 14).
-template <int NH, int CT> struct Cfg { static constexpr int NB = (NH + 1) / 2, WARPS = (NB > 8 || CT == 4) ? 8 : 12; };
+// resident warps per CTA for 8- and 16-column tiles. Measured on config 2 (bench.py, iterations/s): 8 warps 435, 10 warps 443,
+// 12 warps 473, 16 warps (128 registers, small spills) 414 — more warps per scheduler means more DMMAs in front of every
+// chain instruction (profiles/r1_m_scd_stalls.md), fewer leave the pipe idle.
+#ifndef NNLM_SCD_WARPS_NARROW
+#define NNLM_SCD_WARPS_NARROW 12
+#endif
+template <int NH, int CT> struct Cfg { static constexpr int NB = (NH + 1) / 2, WARPS = (NB > 8 || CT == 4) ? 8 : NNLM_SCD_WARPS_NARROW; };
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 {
@@ -151,7 +157,7 @@ k_scd_chain(double* __restrict__ X, const double* __restrict__ G, const double* 
         }
         // multipliers of the first PRE steps of the next block, fetched while the MMAs of step (4) run (narrow tiles have the
         // registers for it): the chain then starts without waiting on shared-memory broadcasts
-        constexpr int PRE = (NB > 8) ? 0 : (CT == 1 ? 7 : (CT == 2 ? 3 : 0));
+        constexpr int PRE = (NB > 8) ? 0 : (WARPS > 12 ? (CT == 1 ? 3 : 0) : (CT == 1 ? 7 : (CT == 2 ? 3 : 0)));
         double wn[PRE ? widx(PRE, PRE + 1) : 1];
 #pragma unroll
         for (int c = 0; c < PRE; c++)
