@@ -96,6 +96,7 @@ k_solve_kl(double* __restrict__ X, const double* __restrict__ Yr, const TA* __re
         // wh = Yr' h  (base_algorithms.cpp:82,133)
         for_owned([&](int64_t i, double& w) {
             double s = 0.0;
+#pragma unroll 8
             for (int c = 0; c < k; c++) s = fma(Yr[(int64_t)c * len + i], hs[c], s);
             w = s;
         });
@@ -113,13 +114,11 @@ k_solve_kl(double* __restrict__ X, const double* __restrict__ Yr, const TA* __re
                 double pa = 0.0, pb = 0.0, ps = 0.0;
                 const bool need_sw = with_missing && t == 0;
                 const int pc = pend_c;
-                for_owned([&](int64_t i, double& wref) {
-                    double w = wref;
-                    if (pc >= 0) { w = fma(pend_d, yp[i], w); wref = w; }
-                    const TA av = Aj[i];
+                auto entry = [&](double w, double ypv, TA av, double y, double& wout) {
+                    if (pc >= 0) w = fma(pend_d, ypv, w);
+                    wout = w;
                     if (with_missing && missing_val<TA>(av)) return;
                     const double a = static_cast<double>(av);
-                    const double y = yc[i];
                     if (METHOD == 3) {
                         const double mu = y / (w + TINY_NUM);               // :97
                         pa = fma(a, mu * mu, pa);                             // dot(Aj, square(mu))
@@ -128,7 +127,40 @@ k_solve_kl(double* __restrict__ X, const double* __restrict__ Yr, const TA* __re
                         pa = fma(y, a / (w + TINY_NUM), pa);                 // :141
                     }
                     if (need_sw) ps += y;
-                });
+                };
+                if (REGS) {
+#pragma unroll
+                    for (int r = 0; r < WHR; r++) {
+                        const int64_t i = threadIdx.x + (int64_t)r * NT;
+                        if (i < len) entry(whr[r], pc >= 0 ? yp[i] : 0.0, Aj[i], yc[i], whr[r]);
+                    }
+                } else {
+                    // four entries per thread and trip, every load issued before the first use: the rolled loop paid the
+                    // L2 latency of its four loads once per entry (memory-latency-bound at 8 warps per scheduler)
+                    constexpr int UNR = 4;
+                    for (int64_t i0 = threadIdx.x; i0 < len; i0 += (int64_t)NT * UNR) {
+                        double w[UNR], ypv[UNR], y[UNR];
+                        TA av[UNR];
+#pragma unroll
+                        for (int u = 0; u < UNR; u++) {
+                            const int64_t i = i0 + (int64_t)u * NT;
+                            const bool in = i < len;
+                            w[u] = in ? whg[i] : 0.0;
+                            ypv[u] = (in && pc >= 0) ? yp[i] : 0.0;
+                            av[u] = in ? Aj[i] : TA(0);
+                            y[u] = in ? yc[i] : 0.0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < UNR; u++) {
+                            const int64_t i = i0 + (int64_t)u * NT;
+                            if (i < len) {
+                                double wout;
+                                entry(w[u], ypv[u], av[u], y[u], wout);
+                                if (pc >= 0) whg[i] = wout;
+                            }
+                        }
+                    }
+                }
                 pend_c = -1;
                 if (need_sw) {
                     const Red2 r2 = block_sum2(ps, 0.0, red);
