@@ -41,7 +41,7 @@ template <> __device__ __forceinline__ bool missing_v<float>(float v) { return (
 
 // Kernel A: the regularised per-column Grams of columns [col0, col0 + ncol) -> Gout[j][k*k] (column-major k x k each).
 template <int RPL, typename TA>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, RPL <= 2 ? 3 : 1)
 k_gram_missing(const double* __restrict__ Y, const TA* __restrict__ A, const double* __restrict__ Gfull,
                const uint8_t* __restrict__ mask, int k, int64_t len, int64_t col0, int64_t ncol, double p0, double p1,
                double* __restrict__ Gout)
