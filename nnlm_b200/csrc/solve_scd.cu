@@ -24,10 +24,12 @@ void launch_scd_tpc(double* X, const double* G, const double* Qp, int splits, co
     // Tile width, measured at 50000 x 10000, k = 50 with scd_chain (bench.py, ANLS iterations/s with 8- / 16- / 32-column
     // tiles on both halves: 371 / 458 / 418): 16 columns per warp keeps 12 warps per SM resident at 168 registers and
     // amortises the sequential part over twice the columns of the 8-column tile; 32 columns need 255 registers (8 warps)
-    // and run two unbalanced rounds. Below 16 x 148 x 12 columns (fewer 16-column groups than resident warps) the
-    // 8-column tile gives every scheduler a second warp to overlap with and wins (H-half, 10000 columns: 466 vs 458 iters/s). NNLM_SCD_CT / NNLM_SCD_CT2_MIN override (experiments).
+    // and run two unbalanced rounds. On smaller shards the 8-column tile gives every scheduler more warps to overlap and wins:
+    // measured per iteration (scratch/ct_threshold.py, W/H columns per GPU): 12500/2500 0.708 ms with 8-column tiles vs 0.765 with
+    // 16-column tiles on the W side; 25000/5000 1.153 vs 1.054 ms; H side of 10000 columns 466 vs 458 iters/s for the 8-column
+    // tile. The switch sits at 16 x 148 x 8 = 18944 columns. NNLM_SCD_CT / NNLM_SCD_CT2_MIN override (experiments).
     static const int force_ct = [] { const char* e = getenv("NNLM_SCD_CT"); return e ? atoi(e) : 0; }();
-    static const int64_t ct2_min = [] { const char* e = getenv("NNLM_SCD_CT2_MIN"); return e ? atoll(e) : (int64_t)16 * 148 * 12; }();
+    static const int64_t ct2_min = [] { const char* e = getenv("NNLM_SCD_CT2_MIN"); return e ? atoll(e) : (int64_t)16 * 148 * 8; }();
     int ct = ncol >= ct2_min ? 2 : 1;
     if (force_ct == 1 || force_ct == 2 || force_ct == 4) ct = force_ct;
     auto fn = ct == 4 ? (nh <= 8 ? scd_chain::launch_ct4_lo : scd_chain::launch_ct4_hi)

@@ -1,5 +1,5 @@
 """The blocked SCD solver picks its tile width from the number of columns (nnlm_b200/csrc/solve_scd.cu): the 16-column tile
-only runs from 16 x 148 x 12 = 28416 columns on, which none of the other parity tests reach. One half-iteration (src/update_with_missing.cpp:3-55
+only runs from 16 x 148 x 8 = 18944 columns on, which none of the other parity tests reach. One half-iteration (src/update_with_missing.cpp:3-55
 + src/base_algorithms.cpp:3-37) on wide, short problems against the oracle, for ranks on both sides of every padding boundary
 (k mod 8, k mod 4) and with coordinate masks."""
 import numpy as np
