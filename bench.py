@@ -248,6 +248,15 @@ def main():
                                   "profiles/r1_n_final_build.md") if (world == 1 and not args.small and args.config == 2) else None,
                 "share_of_step": {"cross": st["cross_ms"] / dev_ms, "solve": st["solve_ms"] / dev_ms,
                                   "gram": st["gram_ms"] / dev_ms, "comm": st["comm_ms"] / dev_ms}}
+    # second roofline, for the kernel with the largest share of the step: the SCD solve is bound by the fp64 pipe (DFMA and
+    # DMMA share it: 64 FMA/clk/SM, measured 63.8 with scratch/dmma_bench.cu). Algorithmic work = k*k FMA per column sweep.
+    if wl["method"] == 1 and wl["na"] == 0.0 and st["solve_ms"] > 0:
+        sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+        fp64_peak = 64.0 * 148 * sm_mhz * 1e6 / 1e12                       # TFMA/s per GPU
+        solve_tfma = float(sweeps) * k * k / world / (st["solve_ms"] * 1e-3) / 1e12
+        roofline["solve"] = {"bound": "fp64 pipe", "achieved": solve_tfma, "peak": fp64_peak, "unit": "TFMA/s",
+                             "frac": solve_tfma / fp64_peak, "kernel": "k_scd_chain (both halves), per GPU",
+                             "peak_source": "64 FMA/clk/SM x 148 SMs x sampled SM clock (DMMA.8x8x4 measured at 63.8, profiles/r1_m_scd_stalls.md)"}
     launches = int(sum_over_ranks(float(st["launches"])))
     sess.close()
 
