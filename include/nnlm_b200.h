@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define NNLM_B200_ABI_VERSION 1
+#define NNLM_B200_ABI_VERSION 2
 
 /* status codes */
 #define NNLM_OK             0
@@ -50,10 +50,18 @@ extern "C" {
 #define NNLM_SCD_MKL 3
 #define NNLM_LEE_MKL 4
 
-/* precision policy of the device copy of A (see DESIGN.md "data layout"):
- *   0 auto  : f64 storage + fp64 CUDA-core contraction when n*m is small, otherwise f32 storage + tcgen05 3xTF32
- *   1 exact : A kept in f64, every product in fp64 (bit-for-bit the reference's arithmetic type)
- *   2 fast  : A kept in f32, cross-products on tcgen05 (3xTF32 split, fp32 TMEM accumulate, fp64 reduction)  */
+/* precision policy of the device copy of A:
+ *   1 exact : A kept in f64, every product and sum in fp64 (the reference's arithmetic type); results agree with the
+ *             reference to ~1e-13 on well-conditioned problems.
+ *   2 fast  : square-loss methods on dense A: A kept as two fp16 planes, (A - mean)*s = hi + lo*2^-11 (22-24 significant
+ *             bits, 4 B/element), cross-products on tcgen05 (3 fp16 MMAs per step, fp32 TMEM accumulators drained into fp64
+ *             every 1024 contraction indices); measured error of the cross-product 1e-10..1e-9 relative to sum|F||A|, of
+ *             the factors after one iteration ~1e-7 (tests/test_gpu_cross.py, tests/test_gpu_scale_parity.py).
+ *             KL methods and the NA path keep A in f32 (relative rounding 6e-8) with every product and sum in fp64.
+ *             Solver state (Gram, mu, h) is fp64 in every mode.
+ *   0 auto  : nnlm_nnmf / sessions: fast when n*m >= 4e6, exact below. nnlm_nnlm and nnlm_update: always exact (their
+ *             callers ask for rel_tol down to 1e-12, R/nnlm.R:72).
+ * The R shim reads NNLM_B200_PRECISION = exact | fast | auto (default auto).                                          */
 #define NNLM_PREC_AUTO  0
 #define NNLM_PREC_EXACT 1
 #define NNLM_PREC_FAST  2
@@ -61,15 +69,26 @@ extern "C" {
 /* Called between half-iterations on the calling thread; return non-zero to abort (-> NNLM_E_INTERRUPT). */
 typedef int (*nnlm_interrupt_fn)(void* user);
 
+/* Sink for the verbose == 2 iteration table of src/nnmf.cpp:100-104,155-156,194-198 (the R shim passes a wrapper of
+ * Rprintf so the text lands on R's console); NULL = stdout. Called on the calling thread only. */
+typedef void (*nnlm_print_fn)(void* user, const char* text);
+
 /* Optional knobs that have no counterpart in the reference signature. Zero-initialise for defaults. */
 typedef struct nnlm_options {
     int32_t precision;        /* NNLM_PREC_*                                                       */
-    int32_t device;           /* CUDA device ordinal, -1 = current                                 */
+    int32_t device;           /* CUDA device ordinal (the first one when n_gpus > 1), -1 = current */
     int32_t verbose_timing;   /* 1 = fill the timing fields of nnlm_stats                          */
-    int32_t reserved0;
-    void*   comm;             /* nnlm_comm handle for the column-sharded multi-GPU path, or NULL   */
-    int64_t m_global;         /* sharded path: global number of columns (0 = m)                    */
-    int64_t col_offset;       /* sharded path: first global column held by this rank               */
+    int32_t n_gpus;           /* nnlm_nnmf: 0 = environment NNLM_B200_GPUS (default 1); N > 1 = shard this ONE call over the
+                                 devices device .. device+N-1: the calling thread drives rank 0, N-1 worker threads the
+                                 others, NCCL inside the library (SURVEY.md §8b "Threading"). Ignored when comm is set. */
+    void*   comm;             /* nnlm_comm handle for the one-process-per-GPU sharded sessions, or NULL */
+    nnlm_print_fn print;      /* verbose output sink, NULL = stdout                                */
+    void*   print_user;
+    int32_t mkl_trace;        /* 0 = like the reference: the KL distance is evaluated at every error record
+                                 (src/nnmf.cpp:137-139). 1 = square-loss methods on dense A evaluate it at the FINAL record
+                                 only (earlier records hold NaN): their target error needs only the MSE, which comes from
+                                 quantities already on the device (Engine::errors), so tracing costs no pass over A. */
+    int32_t reserved1;
 } nnlm_options;
 
 typedef struct nnlm_stats {
@@ -92,6 +111,9 @@ typedef struct nnlm_stats {
     double host_setup_ms;     /* host wall clock: allocation + upload + ingest + factor/mask set-up  */
     double host_loop_ms;      /* host wall clock of the outer loop (incl. error evaluations)        */
     double host_finish_ms;    /* host wall clock: download of W, H                                  */
+    double host_total_ms;     /* host wall clock from entry to just before return (set-up + loop + finish + teardown) */
+    int32_t n_gpus_used;      /* devices this call ran on                                           */
+    int32_t mse_from_identity;/* 1 = the traced MSE came from ||A||^2 - 2<H,WtA> + <WtW,HHt> (no pass over A) */
 } nnlm_stats;
 
 /* ---- c_nnmf (src/nnmf.cpp:4-220) -------------------------------------------------------------
@@ -164,8 +186,8 @@ int nnlm_session_create(nnlm_session** out, const double* A, int64_t n, int64_t 
                         const nnlm_options* opt, char* err, size_t errlen);
 /* Synthetic workload of BASELINE.md §4 generated directly in HBM (the matrix never exists on the host):
  *   A = u(base+1)(n x K) * u(base+2)(K x m) + noise * u(base+3),  entry NaN iff u(base+4) < na_frac,
- *   u(seed, idx) = (splitmix64(seed*0x9E3779B97F4A7C15 + idx) >> 11) * 2^-53, idx = i + n*j with j the global column
- *   (opt->col_offset selects the shard). nnlm_synth_matrix writes the same matrix to host memory. */
+ *   u(seed, idx) = (splitmix64(seed*0x9E3779B97F4A7C15 + idx) >> 11) * 2^-53, idx = i + n*j (global indices; with
+ *   opt->comm every rank generates exactly its column and row shard). nnlm_synth_matrix writes the same matrix to host memory. */
 int nnlm_session_create_synthetic(nnlm_session** out, int64_t n, int64_t m, int32_t K, uint64_t seed_base, double noise,
                                   double na_frac, const double* alpha, const double* beta,
                                   uint32_t inner_max_iter, double inner_rel_tol, int32_t method,
@@ -188,6 +210,10 @@ int nnlm_session_run(nnlm_session* s, uint32_t iters, double* device_ms, int64_t
                      char* err, size_t errlen);
 /* mse / mkl / target (with penalties) of the resident factors: src/nnmf.cpp:121-149, 224-240 */
 int nnlm_session_error(nnlm_session* s, double* mse, double* mkl, double* target, char* err, size_t errlen);
+/* the MSE alone. On the dense square-loss path, right after nnlm_session_run, it is formed from quantities the last
+ * H-half left on the device, ||A||^2 - 2<H,WtA> + <WtW,HHt> (fp64, no pass over A; *from_identity = 1); otherwise it
+ * falls back to the fused pass of nnlm_session_error (*from_identity = 0). SURVEY.md §8f-2, src/nnmf.cpp:135-140. */
+int nnlm_session_mse(nnlm_session* s, double* mse, int32_t* from_identity, char* err, size_t errlen);
 int nnlm_session_stats(nnlm_session* s, nnlm_stats* stats);
 int nnlm_session_reset_stats(nnlm_session* s);   /* zero the timing / launch counters */
 void nnlm_session_destroy(nnlm_session* s);
@@ -204,6 +230,8 @@ void nnlm_comm_destroy(nnlm_comm* c);
 
 /* ---- misc ------------------------------------------------------------------------------------ */
 int nnlm_abi_version(void);
+/* sizeof(nnlm_options) for which == 0, sizeof(nnlm_stats) for which == 1 (bindings check their mirrors against it) */
+size_t nnlm_sizeof(int which);
 /* number of visible CUDA devices (0 if none / no driver); fills name of device 0 when name != NULL */
 int nnlm_device_count(char* name, size_t namelen);
 /* bit-exact NA mask (src/update_with_missing.cpp:80-83,91): builds on the device the bit-plane

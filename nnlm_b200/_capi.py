@@ -25,7 +25,8 @@ INTERRUPT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
 
 class Options(C.Structure):
     _fields_ = [("precision", C.c_int32), ("device", C.c_int32), ("verbose_timing", C.c_int32),
-                ("reserved0", C.c_int32), ("comm", C.c_void_p), ("m_global", C.c_int64), ("col_offset", C.c_int64)]
+                ("n_gpus", C.c_int32), ("comm", C.c_void_p), ("print", C.c_void_p), ("print_user", C.c_void_p),
+                ("mkl_trace", C.c_int32), ("reserved1", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -35,7 +36,8 @@ class Stats(C.Structure):
                 ("precision_used", C.c_int32), ("reserved0", C.c_int32),
                 ("gram_ms", C.c_double), ("cross_launches", C.c_uint64), ("solve_launches", C.c_uint64),
                 ("comm_ms", C.c_double), ("comm_bytes", C.c_uint64),
-                ("host_setup_ms", C.c_double), ("host_loop_ms", C.c_double), ("host_finish_ms", C.c_double)]
+                ("host_setup_ms", C.c_double), ("host_loop_ms", C.c_double), ("host_finish_ms", C.c_double),
+                ("host_total_ms", C.c_double), ("n_gpus_used", C.c_int32), ("mse_from_identity", C.c_int32)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_ if not f.startswith("reserved")}
@@ -55,9 +57,9 @@ _lib = None
 
 # every symbol include/nnlm_b200.h declares (tests/test_abi.py checks the library exports each of them)
 SYMBOLS = [
-    "nnlm_abi_version", "nnlm_device_count", "nnlm_nnmf", "nnlm_nnlm", "nnlm_update", "nnlm_na_mask", "nnlm_cross",
+    "nnlm_abi_version", "nnlm_sizeof", "nnlm_device_count", "nnlm_nnmf", "nnlm_nnlm", "nnlm_update", "nnlm_na_mask", "nnlm_cross",
     "nnlm_session_create", "nnlm_session_create_synthetic", "nnlm_session_create_sharded", "nnlm_synth_block", "nnlm_session_set_factors", "nnlm_session_get_factors",
-    "nnlm_session_run", "nnlm_session_error", "nnlm_session_stats", "nnlm_session_reset_stats", "nnlm_session_destroy",
+    "nnlm_session_run", "nnlm_session_error", "nnlm_session_mse", "nnlm_session_stats", "nnlm_session_reset_stats", "nnlm_session_destroy",
     "nnlm_synth_matrix",
     "nnlm_comm_unique_id", "nnlm_comm_init", "nnlm_comm_destroy",
 ]

@@ -131,20 +131,28 @@ class Nnlm:
     options: dict = field(default_factory=dict)
 
 
-def _options(precision, device):
+def _options(precision, device, n_gpus=0, mkl_trace="all"):
     o = K.Options()
     o.precision = int(precision)
     o.device = int(device)
+    o.n_gpus = int(n_gpus)
+    if mkl_trace not in ("all", "final"):
+        raise ValueError("mkl_trace must be 'all' or 'final'")
+    o.mkl_trace = 1 if mkl_trace == "final" else 0
     return o
 
 
 def nnmf(A, k=1, alpha=(0.0, 0.0, 0.0), beta=(0.0, 0.0, 0.0), method="scd", loss="mse", init=None, mask=None,
          W_norm=-1, check_k=True, max_iter=500, rel_tol=1e-4, n_threads=1, trace=None, verbose=0, show_warning=True,
-         inner_max_iter=None, inner_rel_tol=1e-9, *, rng=None, interrupt=None, precision=K.PREC_AUTO, device=-1):
+         inner_max_iter=None, inner_rel_tol=1e-9, *, rng=None, interrupt=None, precision=K.PREC_AUTO, device=-1, n_gpus=0,
+         mkl_trace="all"):
     """Non-negative matrix factorisation A ~ W H by alternating NNLS — R/nnmf.R:135-225 over nnlm_nnmf (c_nnmf).
 
     Extra keyword-only arguments (no counterpart in R): rng (numpy Generator for the default init — R's RNG stream is not
-    reproduced), interrupt (callable polled once per outer iteration, like Rcpp::checkUserInterrupt), precision, device.
+    reproduced), interrupt (callable polled once per outer iteration, like Rcpp::checkUserInterrupt), precision, device,
+    n_gpus (0 = environment NNLM_B200_GPUS or 1; N > 1 shards this one call over N GPUs inside the library), mkl_trace
+    ('all' = the reference: KL distance at every error record; 'final' = square-loss methods evaluate it for the last
+    record only, earlier entries of `mkl` are NaN and tracing costs no pass over A).
     """
     code = get_method_code(method, loss)
     if inner_max_iter is None:
@@ -203,7 +211,7 @@ def nnmf(A, k=1, alpha=(0.0, 0.0, 0.0), beta=(0.0, 0.0, 0.0), method="scd", loss
     n_err = C.c_uint32(0); n_iter = C.c_uint32(0); conv = C.c_int32(0)
     err = C.create_string_buffer(512)
     stats = K.Stats()
-    opt = _options(precision, device)
+    opt = _options(precision, device, n_gpus, mkl_trace)
     cb = K.INTERRUPT_FN(lambda _u: 1 if interrupt() else 0) if interrupt is not None else K.INTERRUPT_FN()
     t0 = time.perf_counter()
     rc = K.lib().nnlm_nnmf(K.d(A), C.c_int64(n), C.c_int64(m), C.c_int32(Kt), K.d(W), K.d(H), K.i32(Wm), K.i32(Hm),
@@ -291,6 +299,28 @@ def nnlm(x, y, alpha=(0.0, 0.0, 0.0), method="scd", loss="mse", init=None, mask=
     out = coef[:, 0].copy() if is_y_vector else coef
     return Nnlm(coefficients=out, n_iteration=int(nit.value), error=e,
                 options=dict(method=method, loss=loss, max_iter=max_iter, rel_tol=rel_tol))
+
+
+def predict(obj: Nnmf, newdata=None, which="A", method=None, loss=None, **kw):
+    """predict.nnmf — R/nnmf_methods.R:22-48: 'A' returns W H; 'W' / 'H' solve for new rows / columns with nnlm()."""
+    if which not in ("A", "W", "H"):
+        raise ValueError("'arg' should be one of 'A', 'W', 'H'")
+    method = method or obj.options.get("method", "scd")
+    loss = loss or obj.options.get("loss", "mse")
+    if which == "A":
+        return obj.W @ obj.H
+    x = np.asarray(newdata, dtype=np.float64)
+    if x.ndim != 2:
+        raise ValueError("Matrix newdata must be numeric.")
+    if which == "W":
+        if x.shape[1] != obj.H.shape[1]:
+            raise ValueError(f"Dimension of matrix newdata is expected to be (NA, {obj.H.shape[1]}), but got {x.shape}")
+        out = nnlm(obj.H.T, x.T, method=method, loss=loss, **kw)
+        out.coefficients = out.coefficients.T
+        return out
+    if x.shape[0] != obj.W.shape[0]:
+        raise ValueError(f"Dimension of matrix newdata is expected to be ({obj.W.shape[0]}, NA), but got {x.shape}")
+    return nnlm(obj.W, x, method=method, loss=loss, **kw)
 
 
 def nnlm_update(H, Wt, A, mask=None, beta=(0.0, 0.0, 0.0), max_iter=10, rel_tol=1e-8, n_threads=1, method=1,

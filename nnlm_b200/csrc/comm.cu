@@ -21,10 +21,12 @@ struct NcclApi {
     const char* (*GetErrorString)(int) = nullptr;
 };
 
-NcclApi& api()
+// resolved exactly once, also under concurrent first use (the worker threads of a multi-GPU nnlm_nnmf call): a
+// function-local static is initialised under the C++11 guard, and a failed load throws out of the initialiser so the
+// next caller retries
+NcclApi load_api()
 {
-    static NcclApi a;
-    if (a.handle) return a;
+    NcclApi a;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* nm : names) {
         a.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
@@ -45,6 +47,12 @@ NcclApi& api()
     a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(sym("ncclGroupStart"));
     a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(sym("ncclGroupEnd"));
     a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
+    return a;
+}
+
+NcclApi& api()
+{
+    static NcclApi a = load_api();
     return a;
 }
 

@@ -2,6 +2,7 @@
 #include "engine.cuh"
 
 #include <algorithm>
+#include <cmath>
 
 namespace nnlm {
 
@@ -60,9 +61,12 @@ Engine::Engine(int64_t n, int64_t m, int k, int method, int precision, int devic
     NNLM_REQUIRE(n > 0 && m > 0, "A must have positive dimensions");
     NNLM_REQUIRE(k >= 1, "rank k must be positive");
     NNLM_REQUIRE(method >= 1 && method <= 4, "method code must be 1..4 (R/misc.R:28-35)");
-    if (method <= 2) NNLM_REQUIRE(k <= 128, "square-loss solvers support rank k <= 128");
+    // the real per-method limits, checked once with a clear message (every kernel below is instantiated up to them)
+    if (method <= 2) NNLM_REQUIRE(k <= 128, "nnlm_b200: the square-loss solvers (methods 'scd'/'lee' with loss 'mse') support rank / "
+                                            "predictor count k <= 128");
+    else NNLM_REQUIRE(k <= 256, "nnlm_b200: the KL solvers (loss 'mkl') support rank k <= 256");
     if (device_ < 0) NNLM_CUDA_CHECK(cudaGetDevice(&device_));
-    NNLM_CUDA_CHECK(cudaSetDevice(device_));
+    DeviceGuard guard(device_);              // the caller's current device is restored on return
     const int R = comm_ ? comm_->nranks() : 1, rank = comm_ ? comm_->rank() : 0;
     NNLM_REQUIRE(n >= R && m >= R, "fewer rows or columns than ranks");
     chunk_n_ = ceil_div(n_, R); chunk_m_ = ceil_div(m_, R);
@@ -97,6 +101,7 @@ void Engine::ensure_scratch()
     rowsum_part_.alloc((size_t)gram_splits(big) * k_);
     G_.alloc((size_t)k_ * k_);
     Graw_.alloc((size_t)k_ * k_);
+    G2_.alloc((size_t)k_ * k_);
     sumY_.alloc(k_);
     if (method_ <= 2) {
         size_t q = (size_t)cross_simt_splits(k_, n_, mc_) * k_ * std::max<int64_t>(mc_, 1);
@@ -112,9 +117,9 @@ void Engine::ensure_scratch()
         if (both_sides_) w = std::max(w, solve_kl_scratch_doubles(m_, nr_));
         if (w) wh_.alloc(w);
     }
-    size_t rp = std::max<size_t>((size_t)ingest_part_count(n_, std::max<int64_t>(mc_, 1)) * 2,
+    size_t rp = std::max<size_t>((size_t)ingest_part_count(n_, std::max<int64_t>(mc_, 1)) * INGEST_PART_WIDTH,
                                  (size_t)error_part_count(n_, std::max<int64_t>(mc_, 1)) * 2);
-    if (both_sides_) rp = std::max<size_t>(rp, (size_t)ingest_part_count(std::max<int64_t>(nr_, 1), m_) * 2);
+    if (both_sides_) rp = std::max<size_t>(rp, (size_t)ingest_part_count(std::max<int64_t>(nr_, 1), m_) * INGEST_PART_WIDTH);
     rp = std::max<size_t>(rp, (size_t)stats_part_count(big) * 3);
     red_part_.alloc(rp);
     small_.alloc(16);
@@ -151,17 +156,19 @@ void Engine::ingest_shards(const double* dAcol, const double* dArow)
     NNLM_REQUIRE(!both_sides_ || dArow != nullptr, "the row shard of A is required when both halves run");
     // pass 1: missing-entry count and the constant part of the KL distance (src/nnmf.cpp:64-73), over the column shards
     double* acc = small_.p;
-    NNLM_CUDA_CHECK(cudaMemsetAsync(acc, 0, 2 * sizeof(double), st_));
+    NNLM_CUDA_CHECK(cudaMemsetAsync(acc, 0, INGEST_PART_WIDTH * sizeof(double), st_));
     if (mc_ > 0) {
         launch_ingest<double>(dAcol, n_, mc_, 0, mc_, nullptr, nullptr, red_part_.p, st_);
-        launch_reduce_partials(red_part_.p, ingest_part_count(n_, mc_), 2, acc, st_);
+        launch_reduce_partials(red_part_.p, ingest_part_count(n_, mc_), INGEST_PART_WIDTH, acc, st_);
     }
-    if (comm_) comm_->allreduce_sum_f64(acc, 2, st_);
-    NNLM_CUDA_CHECK(cudaMemcpyAsync(host_small_.p, acc, 2 * sizeof(double), cudaMemcpyDeviceToHost, st_));
+    if (comm_) comm_->allreduce_sum_f64(acc, INGEST_PART_WIDTH, st_);
+    NNLM_CUDA_CHECK(cudaMemcpyAsync(host_small_.p, acc, INGEST_PART_WIDTH * sizeof(double), cudaMemcpyDeviceToHost, st_));
     sync();
-    d2h_bytes += 2 * sizeof(double);
+    d2h_bytes += INGEST_PART_WIDTH * sizeof(double);
     kl_const_sum_ = host_small_.p[0];
     n_missing_ = (int64_t)host_small_.p[1];
+    sum_sq_a_ = host_small_.p[2];
+    q_valid_ = false;
     // pass 2: the resident copies, in the storage the precision policy selects (include/nnlm_b200.h)
     if (precision_req_ == NNLM_PREC_FAST && method_ <= 2 && cross_tc_supported(k_) && !use_missing_path())
         storage_ = Storage::F16X2;
@@ -219,6 +226,7 @@ void Engine::set_factors(const double* W, const double* H)
     DeviceGuard g(device_);
     DevBuf<double> tmp((size_t)n_ * k_);
     NNLM_CUDA_CHECK(cudaMemcpyAsync(tmp.p, W, tmp.bytes(), cudaMemcpyHostToDevice, st_));
+    q_valid_ = false;
     launch_transpose_d(tmp.p, n_, k_, Wt_.p, st_);                          // inplace_trans(W), src/nnmf.cpp:90
     NNLM_CUDA_CHECK(cudaMemcpyAsync(H_.p, H, sizeof(double) * k_ * m_, cudaMemcpyHostToDevice, st_));
     sync();
@@ -228,6 +236,7 @@ void Engine::set_factors(const double* W, const double* H)
 void Engine::set_factors_t(const double* Wt, const double* H)
 {
     DeviceGuard g(device_);
+    q_valid_ = false;
     NNLM_CUDA_CHECK(cudaMemcpyAsync(Wt_.p, Wt, sizeof(double) * k_ * n_, cudaMemcpyHostToDevice, st_));
     NNLM_CUDA_CHECK(cudaMemcpyAsync(H_.p, H, sizeof(double) * k_ * m_, cudaMemcpyHostToDevice, st_));
     sync();
@@ -390,6 +399,8 @@ void Engine::gather(double* full, int64_t chunk_cols)
 void Engine::half_w()
 {
     NNLM_REQUIRE(both_sides_, "this engine was created for the H-half only");
+    DeviceGuard g(device_);
+    q_valid_ = false;
     const void* At = storage_ == Storage::F64 ? (const void*)At64_.p : (const void*)At32_.p;
     // solve W[:, rows of this rank] given the whole H; the Gram partial is over the H columns this rank solved last
     run_half(Half{Wt_.p + (size_t)k_ * r0_, nr_, H_.p, m_, H_.p + (size_t)k_ * c0_, mc_, At,
@@ -399,10 +410,14 @@ void Engine::half_w()
 
 void Engine::half_h()
 {
+    DeviceGuard g(device_);
     const void* A = storage_ == Storage::F64 ? (const void*)A64_.p : (const void*)A32_.p;
     run_half(Half{H_.p + (size_t)k_ * c0_, mc_, Wt_.p, n_, Wt_.p + (size_t)k_ * r0_, nr_, A,
                   has_hm_ ? Hm_.p + (size_t)k_ * c0_ : nullptr, beta_, false});
     gather(H_.p, chunk_m_);
+    // the dense square-loss H-half leaves WtA (split-K slots in Qp_) and the raw Gram of W (Graw_) behind: Engine::errors
+    q_valid_ = method_ <= 2 && !use_missing_path();
+    q_slots_ = storage_ == Storage::F16X2 ? plan_h_.slots : cross_simt_splits(k_, n_, mc_);
 }
 
 void Engine::cross_only(double* Q_host)
@@ -432,25 +447,39 @@ void Engine::cross_only(double* Q_host)
     }
 }
 
-void Engine::errors(ErrorTerms* out)
+void Engine::errors(ErrorTerms* out, bool want_kl)
 {
     DeviceGuard g(device_);
     timer.begin(KernelTimer::ERROR, st_);
     NNLM_CUDA_CHECK(cudaMemsetAsync(small_.p, 0, 2 * sizeof(double), st_));
-    if (mc_ > 0) {
+    const bool identity = !want_kl && q_valid_;
+    if (identity) {
+        // sum (A - W'H)^2 = ||A||^2 - 2 <H, WtA> + <WtW, HHt>: WtA is what the H-half just contracted (its split-K slots are
+        // still in Qp_), WtW its raw Gram; only the k x k Gram of the new H is formed here. All fp64, O(k m + k^2).
+        if (mc_ > 0) launch_dot_factor_cross(H_.p + (size_t)k_ * c0_, Qp_.p, q_slots_, k_, mc_, red_part_.p, small_.p, st_);
+        if (comm_) comm_->allreduce_sum_f64(small_.p, 1, st_);
+        launch_gram(H_.p, k_, m_, nullptr, gram_part_.p, G2_.p, st_);
+        launch_dot_small(Graw_.p, G2_.p, k_ * k_, small_.p + 1, st_);
+    } else if (mc_ > 0) {
         // this rank's columns of A against the whole W and its columns of H
         if (storage_ == Storage::F64) launch_error<double>(A64_.p, Wt_.p, H_.p + (size_t)k_ * c0_, k_, n_, mc_, red_part_.p, small_.p, st_);
         else launch_error<float>(A32_.p, Wt_.p, H_.p + (size_t)k_ * c0_, k_, n_, mc_, red_part_.p, small_.p, st_);
     }
-    if (comm_) comm_->allreduce_sum_f64(small_.p, 2, st_);
+    if (comm_ && !identity) comm_->allreduce_sum_f64(small_.p, 2, st_);
     launch_factor_stats(Wt_.p, k_, n_, red_part_.p, small_.p + 2, st_);
     launch_factor_stats(H_.p, k_, m_, red_part_.p, small_.p + 5, st_);
     timer.end(st_);
     NNLM_CUDA_CHECK(cudaMemcpyAsync(host_small_.p, small_.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, st_));
     sync();
     d2h_bytes += 8 * sizeof(double);
-    out->sum_sq = host_small_.p[0];
-    out->sum_kl = host_small_.p[1];
+    if (identity) {
+        out->sum_sq = sum_sq_a_ - 2.0 * host_small_.p[0] + host_small_.p[1];
+        out->sum_kl = std::nan("");
+    } else {
+        out->sum_sq = host_small_.p[0];
+        out->sum_kl = host_small_.p[1];
+    }
+    last_identity_ = identity;
     for (int i = 0; i < 3; i++) { out->w_stats[i] = host_small_.p[2 + i]; out->h_stats[i] = host_small_.p[5 + i]; }
 }
 

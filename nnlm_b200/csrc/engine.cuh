@@ -90,7 +90,12 @@ public:
 
     void half_w();      // solve for W given H (this rank's rows), then all-gather W
     void half_h();      // solve for H given W (this rank's columns), then all-gather H
-    void errors(ErrorTerms* out);                 // global sums; synchronises the stream
+    // global sums; synchronises the stream. want_kl = false: the KL sum is not needed (sum_kl = NaN) — on the dense square-loss
+    // path sum_sq then comes from ||A||^2 - 2<H, WtA> + <WtW, HHt> (quantities the H-half left on the device, fp64) instead
+    // of a pass over A; it falls back to the fused pass whenever those quantities are not current.
+    void errors(ErrorTerms* out, bool want_kl = true);
+    bool last_mse_from_identity() const { return last_identity_; }
+    double sum_sq_A() const { return sum_sq_a_; }
     // diagnostic: Q = Wt * A (k x m, missing entries of A read as zero) through the cross-product path of the current storage
     void cross_only(double* Q_host);
     uint64_t take_sweeps();                       // read and reset the global total_raw_iter (synchronises)
@@ -157,9 +162,13 @@ private:
     bool has_wm_ = false, has_hm_ = false;
     int64_t n_missing_ = 0;
     double kl_const_sum_ = 0.0;
+    double sum_sq_a_ = 0.0;         // ||A||^2 over the finite entries, global
+    bool q_valid_ = false;          // Qp_ / Graw_ / q_slots_ describe the H-half that produced the current H
+    int q_slots_ = 0;
+    bool last_identity_ = false;
 
     // scratch
-    DevBuf<double> gram_part_, rowsum_part_, G_, Graw_, sumY_, Qp_, Yr_, wh_, red_part_, small_, tpc_scratch_;   // small_: 16 doubles of results
+    DevBuf<double> gram_part_, rowsum_part_, G_, Graw_, G2_, sumY_, Qp_, Yr_, wh_, red_part_, small_, tpc_scratch_;   // small_: 16 doubles of results
     DevBuf<unsigned long long> sweeps_;
     PinnedBuf<double> host_small_;
 };

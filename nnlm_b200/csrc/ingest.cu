@@ -25,10 +25,10 @@ k_ingest(const double* __restrict__ src, int64_t len, int64_t ncol, int64_t j0, 
          TOut* __restrict__ dst_cm, TOut* __restrict__ dst_rm, double* __restrict__ part)
 {
     __shared__ double tile[TILE][TILE + 1];
-    __shared__ double red[2][ROWS];
+    __shared__ double red[3][ROWS];
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int64_t i0 = (int64_t)blockIdx.x * TILE, jj0 = (int64_t)blockIdx.y * TILE;
-    double kl = 0.0, miss = 0.0;
+    double kl = 0.0, miss = 0.0, sq = 0.0;
     const int64_t i = i0 + tx;
 #pragma unroll
     for (int r = ty; r < TILE; r += ROWS) {
@@ -37,7 +37,7 @@ k_ingest(const double* __restrict__ src, int64_t len, int64_t ncol, int64_t j0, 
         if (i < len && jj < jc) {
             a = src[i + len * jj];
             if (is_missing(a)) miss += 1.0;
-            else kl += (a + TINY_NUM) * log(a + TINY_NUM) - a;
+            else { kl += (a + TINY_NUM) * log(a + TINY_NUM) - a; sq = fma(a, a, sq); }
             if (dst_cm) dst_cm[i + len * (j0 + jj)] = store_cast<TOut>(a);
         }
         tile[r][tx] = a;
@@ -53,15 +53,17 @@ k_ingest(const double* __restrict__ src, int64_t len, int64_t ncol, int64_t j0, 
     }
     kl = warp_sum(kl);
     miss = warp_sum(miss);
-    if (tx == 0) { red[0][ty] = kl; red[1][ty] = miss; }
+    sq = warp_sum(sq);
+    if (tx == 0) { red[0][ty] = kl; red[1][ty] = miss; red[2][ty] = sq; }
     __syncthreads();
     if (tx == 0 && ty == 0) {
-        double s0 = 0, s1 = 0;
+        double s0 = 0, s1 = 0, s2 = 0;
 #pragma unroll
-        for (int r = 0; r < ROWS; r++) { s0 += red[0][r]; s1 += red[1][r]; }
+        for (int r = 0; r < ROWS; r++) { s0 += red[0][r]; s1 += red[1][r]; s2 += red[2][r]; }
         const int64_t b = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
-        part[2 * b] = s0;
-        part[2 * b + 1] = s1;
+        part[3 * b] = s0;
+        part[3 * b + 1] = s1;
+        part[3 * b + 2] = s2;
     }
 }
 

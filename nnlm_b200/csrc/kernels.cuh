@@ -16,10 +16,12 @@ namespace nnlm {
 struct IngestStats {          // accumulated over chunks, all in fp64 / exact integers
     double  kl_const_sum;     // sum over finite a of (a+TINY)*log(a+TINY) - a      (src/nnmf.cpp:66-73)
     int64_t n_missing;        // number of non-finite entries                        (src/nnmf.cpp:64)
+    double  sum_sq;           // sum over finite a of a^2 (the ||A||^2 term of the Gram-identity MSE, Engine::errors)
 };
+constexpr int INGEST_PART_WIDTH = 3;   // doubles per partial record of launch_ingest: kl_const, n_missing, sum_sq
 // src: chunk of `jc` columns (col-major, leading dimension len) already on the device.
 // dst_cm (len x ncol, may alias src's parent buffer -> pass nullptr to skip) and dst_rm (ncol x len) receive columns [j0, j0+jc).
-// part: device scratch of at least ingest_part_count(len, jc) * 2 doubles.
+// part: device scratch of at least ingest_part_count(len, jc) * INGEST_PART_WIDTH doubles.
 template <typename TOut>
 void launch_ingest(const double* src, int64_t len, int64_t ncol, int64_t j0, int64_t jc, TOut* dst_cm, TOut* dst_rm,
                    double* part, cudaStream_t st);
@@ -125,6 +127,11 @@ int64_t error_part_count(int64_t n, int64_t m);
 template <typename TA>
 void launch_error(const TA* A, const double* W, const double* H, int k, int64_t n, int64_t m, double* part, double* out,
                   cudaStream_t st);
+// Gram-identity MSE: sum (A - W'H)^2 = ||A||^2 - 2 <H, WtA> + <WtW, HHt>, from quantities the
+// H-half left on the device. out[0] = <X, sum over slots of Qp> (X k x ncol, Qp [slot][ncol][k]); part: stats_part_count doubles.
+void launch_dot_factor_cross(const double* X, const double* Qp, int splits, int k, int64_t ncol, double* part, double* out,
+                             cudaStream_t st);
+void launch_dot_small(const double* a, const double* b, int count, double* out, cudaStream_t st);   // out[0] = <a, b>
 // out[0] = sum X^2, out[1] = sum X, out[2] = sum_i (sum_a X[a,i])^2 = accu(X*X.t())   (src/nnmf.cpp:224-240)
 int64_t stats_part_count(int64_t cols);
 void launch_factor_stats(const double* X, int k, int64_t cols, double* part, double* out, cudaStream_t st);

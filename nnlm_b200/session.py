@@ -53,7 +53,7 @@ class Session:
     def __init__(self, A=None, k=1, method=1, alpha=(0, 0, 0), beta=(0, 0, 0), inner_max_iter=50, inner_rel_tol=1e-9,
                  Wm=None, Hm=None, precision=K.PREC_AUTO, device=-1, synthetic=None, timing=False, comm=None, shards=None,
                  shape=None):
-        """A: host matrix (n x m), or synthetic=dict(n=, m=, seed_base=0, noise=0.1, na_frac=0.0, col_offset=0)."""
+        """A: host matrix (n x m), or synthetic=dict(n=, m=, seed_base=0, noise=0.1, na_frac=0.0)."""
         self._h = C.c_void_p()
         self.k = int(k)
         a = K.vec3(alpha); b = K.vec3(beta)
@@ -66,7 +66,6 @@ class Session:
                 raise ValueError("a sharded session needs synthetic=... or shards=(Acol, Arow) with shape=(n, m)")
         if synthetic is not None:
             self.n, self.m = int(synthetic["n"]), int(synthetic["m"])
-            opt.col_offset = int(synthetic.get("col_offset", 0))
             rc = K.lib().nnlm_session_create_synthetic(
                 C.byref(self._h), C.c_int64(self.n), C.c_int64(self.m), C.c_int32(self.k),
                 C.c_uint64(int(synthetic.get("seed_base", 0))), C.c_double(synthetic.get("noise", 0.1)),
@@ -115,6 +114,13 @@ class Session:
         err = C.create_string_buffer(512)
         K.check(K.lib().nnlm_session_error(self._h, C.byref(mse), C.byref(mkl), C.byref(tgt), err, C.c_size_t(512)), err)
         return mse.value, mkl.value, tgt.value
+
+    def mse(self):
+        """(mse, from_identity): the MSE from the Gram identity when the last H-half's products are current (nnlm_session_mse)."""
+        v = C.c_double(0); f = C.c_int32(0)
+        err = C.create_string_buffer(512)
+        K.check(K.lib().nnlm_session_mse(self._h, C.byref(v), C.byref(f), err, C.c_size_t(512)), err)
+        return v.value, bool(f.value)
 
     def stats(self):
         st = K.Stats()

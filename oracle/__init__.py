@@ -77,6 +77,48 @@ def max_threads() -> int:
     return int(lib().oracle_max_threads())
 
 
+def splitmix_uniform(seed: int, count: int, offset: int = 0) -> np.ndarray:
+    """u(seed, idx) of SURVEY.md §8d (numpy twin of the generators in oracle_synth_block and csrc/synth.cu)."""
+    out = np.empty(count, dtype=np.float64)
+    step = 1 << 24
+    with np.errstate(over="ignore"):
+        for a in range(0, count, step):
+            b = min(count, a + step)
+            z = np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15) + np.arange(offset + a, offset + b, dtype=np.uint64)
+            z = z + np.uint64(0x9E3779B97F4A7C15)
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z = z ^ (z >> np.uint64(31))
+            out[a:b] = (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    return out
+
+
+def set_threads(n: int) -> None:
+    """Set the OpenMP thread count (torchrun exports OMP_NUM_THREADS=1 to its workers; bench.py's reference arm calls
+    this with len(os.sched_getaffinity(0)) so the CPU arm uses all host cores at every N)."""
+    lib().oracle_set_threads(C.c_int(int(n)))
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
+def synth_block(n_global, row0, nr, col0, mc, k, seed_base=0, noise=0.1, na_frac=0.0, n_threads=0):
+    """Host twin of the device generator (nnlm_synth_block): rows [row0,row0+nr) x columns [col0,col0+mc) of the
+    synthetic matrix of SURVEY.md §8d, bit-identical to the GPU arm's matrix."""
+    A = np.empty((nr, mc), dtype=np.float64, order="F")
+    lib().oracle_synth_block(_d(A), C.c_int64(n_global), C.c_int64(row0), C.c_int64(nr), C.c_int64(col0), C.c_int64(mc),
+                             C.c_int32(k), C.c_uint64(seed_base), C.c_double(noise), C.c_double(na_frac), C.c_int32(n_threads))
+    return A
+
+
+def synth_matrix(n, m, k, seed_base=0, noise=0.1, na_frac=0.0, n_threads=0):
+    return synth_block(n, 0, n, 0, m, k, seed_base, noise, na_frac, n_threads)
+
+
 def set_faithful_transpose(on: bool) -> None:
     lib().oracle_set_faithful_transpose(C.c_int(1 if on else 0))
 

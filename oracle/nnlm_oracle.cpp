@@ -396,6 +396,49 @@ void oracle_transpose(const double* A, int64_t n, int64_t m, double* At, int32_t
         }
 }
 
+// Synthetic workload of SURVEY.md §8(d) / BASELINE.md §4 on the host (the twin of the device generator the GPU arm uses, so
+// the CPU reference arm of bench.py needs no GPU library): rows [row0, row0+nr) x columns [col0, col0+mc) of
+//   A = u(base+1)(n_global x k) * u(base+2)(k x m) + noise * u(base+3, i + n_global*j),  NaN iff u(base+4, idx) < na_frac,
+// with u(seed, idx) = (splitmix64(seed*0x9E3779B97F4A7C15 + idx) >> 11) * 2^-53. The inner product is one fused
+// multiply-add chain in coordinate order, exactly as the device kernel forms it, so both generators agree bit for bit.
+static inline double splitmix_u(uint64_t seed, uint64_t idx)
+{
+    uint64_t z = seed * 0x9E3779B97F4A7C15ull + idx;
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+void oracle_synth_block(double* A, int64_t n_global, int64_t row0, int64_t nr, int64_t col0, int64_t mc, int32_t k,
+                        uint64_t base, double noise, double na_frac, int32_t n_threads)
+{
+    const int nt = resolve_threads(n_threads);
+    std::vector<double> Wt((size_t)nr * k);          // [c][i] like the device copy: unit stride along i
+    for (int c = 0; c < k; c++)
+        for (int64_t i = 0; i < nr; i++) Wt[(size_t)c * nr + i] = splitmix_u(base + 1, (uint64_t)(row0 + i) + (uint64_t)n_global * (uint64_t)c);
+    const double nanv = std::nan("");
+    #pragma omp parallel for num_threads(nt) schedule(static)
+    for (int64_t j = 0; j < mc; j++) {
+        std::vector<double> h(k);
+        for (int c = 0; c < k; c++) h[c] = splitmix_u(base + 2, (uint64_t)k * (uint64_t)(col0 + j) + (uint64_t)c);
+        double* Aj = A + (size_t)nr * j;
+        for (int64_t i = 0; i < nr; i++) Aj[i] = 0.0;
+        for (int c = 0; c < k; c++) {
+            const double* w = Wt.data() + (size_t)c * nr;
+            const double hc = h[c];
+            for (int64_t i = 0; i < nr; i++) Aj[i] = std::fma(w[i], hc, Aj[i]);
+        }
+        for (int64_t i = 0; i < nr; i++) {
+            const uint64_t idx = (uint64_t)(row0 + i) + (uint64_t)n_global * (uint64_t)(col0 + j);
+            double s = std::fma(noise, splitmix_u(base + 3, idx), Aj[i]);
+            if (na_frac > 0.0 && splitmix_u(base + 4, idx) < na_frac) s = nanv;
+            Aj[i] = s;
+        }
+    }
+}
+
 int oracle_max_threads(void)
 {
 #ifdef _OPENMP
@@ -406,6 +449,17 @@ int oracle_max_threads(void)
 }
 
 // one half-iteration; same contract as nnlm_update (include/nnlm_b200.h)
+// torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the reference arm of bench.py calls this with the
+// number of cores the process may run on so "all host cores" stays true under torchrun.
+void oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_update(double* H, const double* Wt, const double* A, const int32_t* mask, const double* beta,
                   int32_t k, int64_t n, int64_t m, uint32_t max_iter, double rel_tol, int32_t n_threads,
                   int32_t method, int32_t with_missing, int64_t* total_iter,

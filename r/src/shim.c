@@ -5,9 +5,11 @@
  * R/RcppExports.R, R/nnmf.R and R/nnlm.R of the reference run unmodified on top of it.
  *
  * Plain C against R's own API (no Rcpp, no Armadillo): build with  R CMD SHLIB shim.c -L<dir> -lnnlm_b200 .
- * R is not present in the image this repository is developed in, so this file is compile-checked against
- * r/tests/mock/Rinternals.h only (tests/test_r_shim.py); see INTEGRATION.md.
+ * R is not present in the image this repository is developed in: the file is compile-checked against the declarations of
+ * r/tests/mock/Rinternals.h, and EXECUTED on the GPU box against the miniature runtime r/tests/mock/rmock.c, which
+ * implements just the R API calls used here (r/tests/shim_driver.c, tests/test_r_shim.py); see INTEGRATION.md.
  */
+#include <stdlib.h>
 #include <string.h>
 
 #include <R.h>
@@ -20,6 +22,28 @@
  * iterations and unwinds normally; the shim then raises the R interrupt condition. */
 static void chk_intr(void* dummy) { (void)dummy; R_CheckUserInterrupt(); }
 static int interrupted(void* user) { (void)user; return R_ToplevelExec(chk_intr, NULL) == FALSE; }
+
+/* verbose == 2 table (src/nnmf.cpp:100-104,155-156,194-198) goes to R's console, not to the process's stdout */
+static void print_to_r(void* user, const char* text) { (void)user; Rprintf("%s", text); }
+
+/* Knobs without a counterpart in the reference's R signature come from the environment, so R/nnmf.R stays untouched:
+ *   NNLM_B200_PRECISION = auto | exact | fast      (include/nnlm_b200.h, default auto)
+ *   NNLM_B200_GPUS      = N                        (shard one nnmf() call over N GPUs; read by the library itself)
+ *   NNLM_B200_MKL_TRACE = all | final              (default all = the reference's behaviour)
+ *   NNLM_B200_DEVICE    = CUDA ordinal             (default: current device) */
+static void options_from_env(nnlm_options* opt)
+{
+    memset(opt, 0, sizeof *opt);
+    opt->device = -1;
+    const char* e = getenv("NNLM_B200_PRECISION");
+    if (e && strcmp(e, "exact") == 0) opt->precision = NNLM_PREC_EXACT;
+    else if (e && strcmp(e, "fast") == 0) opt->precision = NNLM_PREC_FAST;
+    e = getenv("NNLM_B200_MKL_TRACE");
+    if (e && strcmp(e, "final") == 0) opt->mkl_trace = 1;
+    e = getenv("NNLM_B200_DEVICE");
+    if (e && *e) opt->device = atoi(e);
+    opt->print = print_to_r;
+}
 
 static const int32_t* mask_or_null(SEXP m) { return XLENGTH(m) > 0 ? (const int32_t*)LOGICAL(m) : NULL; }
 
@@ -69,8 +93,7 @@ SEXP _NNLM_c_nnmf(SEXP A, SEXP kS, SEXP W0, SEXP H0, SEXP Wm, SEXP Hm, SEXP alph
     int32_t converged = 1;
     char err[512];
     nnlm_options opt;
-    memset(&opt, 0, sizeof opt);
-    opt.device = -1;
+    options_from_env(&opt);
     const int rc = nnlm_nnmf(REAL(A), (int64_t)n, (int64_t)m, K, w, h, wm, hm, REAL(alpha), REAL(beta), max_iter,
                              Rf_asReal(rel_tolS), Rf_asInteger(n_threadsS), Rf_asInteger(verboseS),
                              (unsigned)Rf_asInteger(inner_max_iterS), Rf_asReal(inner_rel_tolS), Rf_asInteger(methodS), trace,
@@ -114,8 +137,7 @@ SEXP _NNLM_c_nnlm(SEXP x, SEXP y, SEXP alpha, SEXP mask, SEXP beta0, SEXP max_it
     int64_t nstep = 0;
     char err[512];
     nnlm_options opt;
-    memset(&opt, 0, sizeof opt);
-    opt.device = -1;
+    options_from_env(&opt);
     const int rc = nnlm_nnlm(REAL(x), REAL(y), (int64_t)n, (int64_t)p, (int64_t)q, b, mask_or_null(mask), REAL(alpha),
                              (unsigned)Rf_asInteger(max_iterS), Rf_asReal(rel_tolS), Rf_asInteger(n_threadsS),
                              Rf_asInteger(methodS), &nstep, &opt, NULL, err, sizeof err);

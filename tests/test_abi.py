@@ -35,8 +35,11 @@ def test_abi_version_matches_header():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(K.Options) == 40
-    assert C.sizeof(K.Stats) == 6 * 8 + 3 * 8 + 2 * 4 + 3 * 8 + 2 * 8 + 3 * 8
+    """The ctypes mirrors have the sizes the compiled library reports for its own structs (nnlm_sizeof)."""
+    lib = K.lib()
+    lib.nnlm_sizeof.restype = C.c_size_t
+    assert C.sizeof(K.Options) == lib.nnlm_sizeof(0) == 48
+    assert C.sizeof(K.Stats) == lib.nnlm_sizeof(1) == 160
 
 
 def test_no_cpu_fallback():
