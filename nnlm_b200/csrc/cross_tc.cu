@@ -7,7 +7,7 @@
 //     sum_i A[i,j] F[a,i]  =  ( sum hi_A hi_F  +  2^-11 * sum (hi_A lo_F + lo_A hi_F) ) / (s_A s_F[a])      (+ O(2^-22) dropped)
 // Each product of two fp16 values is exact in the fp32 accumulator; the two sums live in separate TMEM accumulators so
 // the small terms are not rounded against the large ones. Long fp32 accumulation is avoided (the tensor core truncates
-// each accumulate, which biases long sums): every `drain` k-blocks (default 16 = 1024 contraction indices) the accumulators are read out of TMEM and added into fp64 registers, while the tensor core
+// each accumulate, which biases long sums): every `drain` k-blocks (4 = 256 contraction indices; 2 for the 128-row factor tile) the accumulators are read out of TMEM and added into fp64 registers, while the tensor core
 // continues into the other TMEM buffer. Measured error of the whole cross-product vs fp64: see tests/test_gpu_cross.py.
 //
 // Centering. The tensor core truncates every accumulate; with all-positive data that is a systematic bias (measured:
@@ -38,7 +38,14 @@ namespace {
 
 constexpr int BM = 128;          // columns of A per tile
 constexpr int BK = 64;           // fp16 elements per k-block (128 bytes)
-constexpr int DRAIN_DEFAULT = 16; // k-blocks between TMEM drains (1024 contraction indices = 64 MMAs per accumulator)
+// k-blocks accumulated in TMEM between two drains into the fp64 registers. The fp32 accumulation in TMEM is the dominant error
+// of the whole cross-product (measured, 5000 x 2000, contraction length 2000: relative Frobenius error 6.4e-10 / 3.5e-10 /
+// 2.0e-10 / 1.5e-10 at 16 / 4 / 2 / 1 k-blocks per drain); the epilogue hides behind the HBM stream down to 4 k-blocks for the
+// 32- and 64-row factor tiles (cross-product time +0.9 %), and costs 24 % at 2 k-blocks for the 128-row tile, where it buys
+// the 1e-5 parity of the first iteration at k = 128 (the near-rank-one tiny init amplifies the W-half's error ~2000x into H:
+// tests/test_gpu_scale_parity.py, profiles/r2_b_drain_interval.md).
+constexpr int DRAIN_SMALL = 4;    // NP = 32, 64: 256 contraction indices
+constexpr int DRAIN_LARGE = 2;    // NP = 128:    128 contraction indices
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 32 * (2 + EPI_WARPS);
 constexpr float LO_SCALE = 2048.0f;            // 2^11
@@ -519,8 +526,8 @@ void launch_np(const CrossPlan& plan, const __half* a_hi, const __half* a_lo, co
     const CUtensorMap mF_lo = make_map(f_lo, plan.len, NP, plan.ld_f, NP);
     CrossParams p;
     p.ncol = plan.ncol; p.kblocks = plan.kblocks; p.units = plan.units; p.k = plan.k; p.Qp = Qp; p.unscale = unscale;
-    static const int drain_env = [] { const char* e = getenv("NNLM_TC_DRAIN"); const int v = e ? atoi(e) : 0; return v > 0 ? v : DRAIN_DEFAULT; }();
-    p.drain = drain_env;
+    static const int drain_env = [] { const char* e = getenv("NNLM_TC_DRAIN"); return e ? atoi(e) : 0; }();
+    p.drain = drain_env > 0 ? drain_env : (NP >= 128 ? DRAIN_LARGE : DRAIN_SMALL);
     p.center = center; p.fsum = fsum;
     NNLM_CUDA_CHECK(cudaMemsetAsync(Qp, 0, sizeof(double) * (size_t)plan.slots * plan.ncol * plan.k, st));
     kern<<<plan.grid, THREADS, smem, st>>>(mA_hi, mA_lo, mF_hi, mF_lo, p);

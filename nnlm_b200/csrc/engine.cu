@@ -3,6 +3,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <type_traits>
 
 namespace nnlm {
 
@@ -113,6 +115,7 @@ void Engine::ensure_scratch()
         Qp_.alloc(q);
     } else {
         Yr_.alloc((size_t)k_ * big);
+        Yr32_.alloc((size_t)k_ * big);
         size_t w = solve_kl_scratch_doubles(n_, mc_);
         if (both_sides_) w = std::max(w, solve_kl_scratch_doubles(m_, nr_));
         if (w) wh_.alloc(w);
@@ -349,13 +352,21 @@ void Engine::run_half_t(const Half& h)
             timer.end(st_);
         }
     } else {
+        // fast storage, dense A: the cluster kernel with the column state on chip (solve_kl_fast.cu); otherwise the fp64 kernel
+        const bool fast_kl = std::is_same<TA, float>::value && !missing && solve_kl_fast_supported(k_, h.len)
+                             && std::getenv("NNLM_KL_SLOW") == nullptr;
         timer.begin(KernelTimer::GRAM, st_);
         launch_rowsum(h.Y, k_, h.len, rowsum_part_.p, sumY_.p, st_);                       // :27
-        launch_transpose_d(h.Y, k_, h.len, Yr_.p, st_);
+        if (fast_kl) launch_factor_rows_f32(h.Y, k_, h.len, Yr32_.p, st_);
+        else launch_transpose_d(h.Y, k_, h.len, Yr_.p, st_);
         timer.end(st_);
         timer.begin(KernelTimer::SOLVE, st_);
-        launch_solve_kl<TA>(method_, h.X, Yr_.p, A, sumY_.p, h.mask, k_, h.len, h.ncol, h.pen, inner_max_iter_,
-                            inner_rel_tol_, missing ? 1 : 0, wh_.p, sweeps_.p, st_);
+        if (fast_kl)
+            launch_solve_kl_fast(method_, h.X, Yr32_.p, reinterpret_cast<const float*>(A), sumY_.p, h.mask, k_, h.len, h.ncol, h.pen,
+                                 inner_max_iter_, inner_rel_tol_, sweeps_.p, st_);
+        else
+            launch_solve_kl<TA>(method_, h.X, Yr_.p, A, sumY_.p, h.mask, k_, h.len, h.ncol, h.pen, inner_max_iter_,
+                                inner_rel_tol_, missing ? 1 : 0, wh_.p, sweeps_.p, st_);
         timer.end(st_);
     }
 }

@@ -120,6 +120,14 @@ void launch_solve_kl(int method, double* X, const double* Yr, const TA* A, const
                      int64_t len, int64_t ncol, const double* pen, unsigned max_iter, double rel_tol, int with_missing,
                      double* wh_scratch, unsigned long long* sweeps, cudaStream_t st);
 
+// ---- solve_kl_fast.cu: K7/K8 with the column state on chip (fast-precision path: dense A in fp32, no missing entries) ----
+// Y32 is the fp32 row-major copy of the fixed factor ([k][len], launch_factor_rows_f32); see the file header for the design.
+bool solve_kl_fast_supported(int k, int64_t len);
+void launch_factor_rows_f32(const double* Y, int k, int64_t len, float* out, cudaStream_t st);
+void launch_solve_kl_fast(int method, double* X, const float* Y32, const float* A, const double* sumY, const uint8_t* mask, int k,
+                          int64_t len, int64_t ncol, const double* pen, unsigned max_iter, double rel_tol,
+                          unsigned long long* sweeps, cudaStream_t st);
+
 // ---- error_eval.cu: a8/a9 ----
 // Sums over finite entries of A of (A - W'H)^2 and of -(A+TINY)*log(W'H+TINY) + W'H  (src/nnmf.cpp:121-141).
 // W is k x n, H is k x m, A is n x m. out[0] = sum sq, out[1] = sum kl. part: scratch error_part_count()*2 doubles.

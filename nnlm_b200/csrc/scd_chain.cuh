@@ -6,11 +6,14 @@
 // ran at ~250 cycles per step because every step waited on shared-memory broadcasts of V, a second dependent chain (the
 // short-circuit convergence test) shared the in-order issue slot, and the chain's DFMAs queued behind other warps' DMMAs.
 // Here:
-//   * the chain never touches mu. At block entry P_r = h_r - mu_r / V_rr (the unclamped candidates; the division is a
-//     multiplication done on the fragments before the tile is transposed) are formed for the 8
-//     coordinates; step c reads cand = P_c, derives d_c, and folds it into the later candidates with ONE fma per row,
-//     P_r -= (V_rc / V_rr) d_c  (r > c, multipliers precomputed per half-iteration). Dependent path per step:
-//     DFMA -> {sign test || DADD} -> select -> select(mask) instead of DFMA -> clamp -> DADD -> mask -> DFMA;
+//   * the chain never touches mu. At block entry P_r = h_r - mu'_r / V_rr are formed for the 8 coordinates, where the MMA
+//     side maintains mu' = mu - L h with L the strictly lower triangle of the block's own 8x8 diagonal tile of V (the Gram
+//     copy the MMAs read has those entries zeroed), so P_r already holds + (V_rc / V_rr) h_c(old) for the earlier
+//     coordinates c of the block. Step c reads cand = P_c, clamps it to the new value hn_c and folds it into the later
+//     candidates with ONE fma per row, P_r -= (V_rc / V_rr) hn_c (r > c, multipliers precomputed per half-iteration).
+//     Dependent path per step: DFMA -> sign test -> select -> DFMA (round 1 had DFMA -> DADD -> select -> select -> DFMA:
+//     two fp64-pipe instructions per step queueing behind the neighbours' DMMAs instead of one); d = hn - hc, which the
+//     MMAs and the exit test need, is computed off that path;
 //   * all of mu, the diagonal tile included, takes the block's eight rank-1 updates as DMMA.8x8x4 afterwards (full fp64
 //     rate, operands straight from fragments): the next diagonal tile first, so its transposition to one-thread-per-column
 //     overlaps the remaining MMAs;
@@ -18,7 +21,7 @@
 // fp64 pipe budget per block and 32 columns: 56 DMMA x 16 cycles + ~70 DFMA-class x 2 cycles (DFMA/DMMA share one pipe at
 // 64 FMA/clk/SM: scratch/mix_bench.cu). Arithmetic differences from the reference, all at rounding level: reciprocal and
 // pre-multiplied V_rc/V_rr instead of a division per step; the candidate of coordinate r inside a block is accumulated
-// as h_r - mu_r/V_rr - sum_c (V_rc/V_rr) d_c instead of through mu; `tmp != Hj(k)` becomes d = 0; the exit test
+// as h_r - mu'_r/V_rr - sum_c (V_rc/V_rr) hn_c instead of through mu; `tmp != Hj(k)` becomes d = 0; the exit test
 // 2|d|/(h_new+h_old+1e-16) > tol is evaluated as |d| - (tol/2)(h_new+h_old) > (tol/2)1e-16.
 // Control flow per column is the reference's (stop when the max relative change <= rel_tol or at max_iter; finished
 // columns are frozen while the rest of the tile keeps sweeping); sweep counts are summed into total_raw_iter.
@@ -78,6 +81,16 @@ k_scd_chain(double* __restrict__ X, const double* __restrict__ G, const double* 
     for (int e = threadIdx.x; e < NB * 64; e += 32 * WARPS) {
         const int b = e >> 6, c = (e >> 3) & 7, r = e & 7;
         if (r > c) wl[b * 32 + woff(c) + (r - c - 1)] = rinv[8 * b + r] * gc[(8 * b + c) * KS + 8 * b + r];
+    }
+    __syncthreads();
+    // From here on the MMA side works with V' = V minus the strictly lower triangle of every diagonal 8x8 block, i.e. it
+    // maintains mu'_r = mu_r - sum_{c < r, same block} V_rc h_c. The candidates formed from it,
+    // P_r = h_r - mu'_r / V_rr = h_r - mu_r / V_rr + sum_{c<r} (V_rc / V_rr) h_c(old), already contain the old h of the
+    // earlier coordinates of the block, so a chain step folds in the NEW value with one FMA, P_r -= (V_rc / V_rr) hn_c,
+    // and the difference d = hn - hc is off the dependent path (it is only published for the MMAs and the exit test).
+    for (int e = threadIdx.x; e < NB * 64; e += 32 * WARPS) {
+        const int b = e >> 6, c = (e >> 3) & 7, r = e & 7;
+        if (r > c) gc[(8 * b + c) * KS + 8 * b + r] = 0.0;
     }
     __syncthreads();
 
@@ -201,17 +214,15 @@ k_scd_chain(double* __restrict__ X, const double* __restrict__ G, const double* 
                     for (int c = 0; c < 8; c++) {
                         const int cc = 8 * b + c;
                         const double cand = P[c], hc = h8[c];
-                        const bool neg = __double2hiint(cand) < 0;
                         const bool live = !((fz[cc >> 6] >> (cc & 63)) & 1ull);
-                        const double dpos = cand - hc;
-                        double d = neg ? flip_sign(hc) : dpos;                 // integer sign flip: keeps the fp64 pipe for the FMAs
-                        double hn = neg ? 0.0 : cand;
-                        d = live ? d : 0.0;
-                        hn = live ? hn : hc;
+                        const double alt = live ? 0.0 : hc;                    // what h becomes when the candidate is not taken
+                        const bool take = live && !(__double2hiint(cand) < 0); // dependent path: DFMA -> sign test -> select -> DFMA
+                        const double hn = take ? cand : alt;
+                        const double d = hn - hc;                              // off the dependent path
                         dd[c] = d;
                         h8[c] = hn;
 #pragma unroll
-                        for (int r = c + 1; r < 8; r++) P[r] = fma(-(c < PRE ? wn[widx(c, r)] : wb[woff(c) + (r - c - 1)]), d, P[r]);
+                        for (int r = c + 1; r < 8; r++) P[r] = fma(-(c < PRE ? wn[widx(c, r)] : wb[woff(c) + (r - c - 1)]), hn, P[r]);
                         // 2|d| > tol (hn + hc + 1e-16)  <=>  (tol/2)(hn + hc) + (tol/2)1e-16 - |d| < 0 : collect the sign bits
                         if (decltype(with_flag)::value) flagbits |= __double2hiint(fma(hn + hc, tolh, c0 - fabs(d)));
                         if (NB > 1) {

@@ -1,0 +1,10 @@
+// solve_kl_fast_m3_lo.cu — instantiations of the cluster KL solver (solve_kl_fast.cuh): method 3, 1..8 entries per thread
+#include "solve_kl_fast.cuh"
+
+namespace nnlm { namespace klf {
+void launch_m3_lo(NNLM_KLF_ARGS)
+{
+    if (sh.E < 5) launch_range<3, 1>(NNLM_KLF_PASS);
+    else launch_range<3, 5>(NNLM_KLF_PASS);
+}
+} }
