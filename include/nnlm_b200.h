@@ -59,8 +59,10 @@ extern "C" {
  *             the factors after one iteration ~1e-7 (tests/test_gpu_cross.py, tests/test_gpu_scale_parity.py).
  *             KL methods and the NA path keep A in f32 (relative rounding 6e-8) with every product and sum in fp64.
  *             Solver state (Gram, mu, h) is fp64 in every mode.
- *   0 auto  : nnlm_nnmf / sessions: fast when n*m >= 4e6, exact below. nnlm_nnlm and nnlm_update: always exact (their
- *             callers ask for rel_tol down to 1e-12, R/nnlm.R:72).
+ *   0 auto  : nnlm_nnmf / sessions: exact when n*m < 4e6; otherwise fast, except that dense square-loss problems whose
+ *             largest entry exceeds rms(A) * min(n, m) / 16 (count-like data with isolated huge entries) stay exact — the
+ *             fp32 accumulators lose the small products added after such a spike. nnlm_nnlm and nnlm_update: always exact
+ *             (their callers ask for rel_tol down to 1e-12, R/nnlm.R:72).
  * The R shim reads NNLM_B200_PRECISION = exact | fast | auto (default auto).                                          */
 #define NNLM_PREC_AUTO  0
 #define NNLM_PREC_EXACT 1
@@ -170,6 +172,13 @@ int nnlm_update(double* H, const double* Wt, const double* A, const int32_t* mas
  * the fp64 CUDA-core or the tcgen05 path). Non-finite entries of A are read as zero (the masked product of :91). */
 int nnlm_cross(const double* Wt, const double* A, int32_t k, int64_t n, int64_t m, double* Q,
                const nnlm_options* opt, nnlm_stats* stats, char* err, size_t errlen);
+
+/* ---- diagnostic: the per-column corrections of update_with_missing (src/update_with_missing.cpp:88-91) as the fast path
+ * forms them, by ONE tensor-core contraction of the 0/1 missing mask with the Khatri-Rao self-product of the factor:
+ *   S[j*width + a(a+1)/2 + b] = sum_{i : A[i,j] missing} Wt[a,i] Wt[b,i]  (a >= b),   S[j*width + k(k+1)/2 + a] = sum_{i missing} Wt[a,i]
+ * so that WtW_j = Wt Wt' - S_j. width (returned) = k(k+1)/2 + k rounded up to a multiple of 128. */
+int nnlm_na_corrections(const double* Wt, const double* A, int32_t k, int64_t n, int64_t m, double* S, int64_t s_capacity,
+                        int64_t* width, const nnlm_options* opt, char* err, size_t errlen);
 
 /* ---- device-resident session: the benchmark's "inputs already in HBM" path -------------------
  * nnlm_session_create uploads A once (the copy + layout conversion c_nnmf implies per call);

@@ -57,7 +57,7 @@ _lib = None
 
 # every symbol include/nnlm_b200.h declares (tests/test_abi.py checks the library exports each of them)
 SYMBOLS = [
-    "nnlm_abi_version", "nnlm_sizeof", "nnlm_device_count", "nnlm_nnmf", "nnlm_nnlm", "nnlm_update", "nnlm_na_mask", "nnlm_cross",
+    "nnlm_abi_version", "nnlm_sizeof", "nnlm_device_count", "nnlm_nnmf", "nnlm_nnlm", "nnlm_update", "nnlm_na_mask", "nnlm_cross", "nnlm_na_corrections",
     "nnlm_session_create", "nnlm_session_create_synthetic", "nnlm_session_create_sharded", "nnlm_synth_block", "nnlm_session_set_factors", "nnlm_session_get_factors",
     "nnlm_session_run", "nnlm_session_error", "nnlm_session_mse", "nnlm_session_stats", "nnlm_session_reset_stats", "nnlm_session_destroy",
     "nnlm_synth_matrix",

@@ -357,6 +357,24 @@ def na_mask(A):
     return bits, cols
 
 
+def na_corrections(Wt, A, *, device=-1):
+    """Diagnostic: per-column Gram / row-sum corrections of the NA path from the tensor-core mask contraction
+    (nnlm_na_corrections). Returns (S_pairs m x k(k+1)/2 with pair (a >= b) at a(a+1)/2 + b, S_rows m x k)."""
+    Wt = K.f64(Wt, copy=False); A = K.f64(A, copy=False)
+    k, n = Wt.shape
+    m = A.shape[1]
+    width = (k * (k + 1) // 2 + k + 127) // 128 * 128
+    S = np.empty((m, width), dtype=np.float64)
+    w = C.c_int64(0)
+    err = C.create_string_buffer(512)
+    opt = _options(K.PREC_FAST, device)
+    rc = K.lib().nnlm_na_corrections(K.d(Wt), K.d(A), C.c_int32(k), C.c_int64(n), C.c_int64(m), K.d(S), C.c_int64(S.size),
+                                     C.byref(w), C.byref(opt), err, C.c_size_t(512))
+    K.check(rc, err)
+    kk2 = k * (k + 1) // 2
+    return S[:, :kk2].copy(), S[:, kk2:kk2 + k].copy()
+
+
 def cross(Wt, A, *, precision=K.PREC_AUTO, device=-1):
     """Diagnostic: Q = Wt @ A (non-finite entries of A read as zero) through the library's cross-product kernels."""
     Wt = K.f64(Wt, copy=False); A = K.f64(A, copy=False)

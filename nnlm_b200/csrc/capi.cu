@@ -103,12 +103,13 @@ double penalty_from_stats(const ErrorTerms& t, const double* alpha, const double
     return p;
 }
 
-// AUTO resolves to the tensor-core path only for whole factorisations of large matrices; the single-update entry points
-// (nnlm_nnlm, nnlm_update) are called with tolerances down to 1e-12 and stay in fp64 unless FAST is asked for explicitly
-int precision_of(const nnlm_options* opt, int64_t n, int64_t m, bool factorisation)
+// AUTO: whole factorisations (nnlm_nnmf, sessions) leave the choice to the engine, which knows the size and, after the
+// ingest pass, the data (Engine::ingest_shards). The single-update entry points (nnlm_nnlm, nnlm_update) are called with
+// tolerances down to 1e-12 and stay in fp64 unless FAST is asked for explicitly.
+int precision_of(const nnlm_options* opt, int64_t /*n*/, int64_t /*m*/, bool factorisation)
 {
-    int p = opt ? opt->precision : NNLM_PREC_AUTO;
-    if (p == NNLM_PREC_AUTO) p = (factorisation && (double)n * (double)m >= 4.0e6) ? NNLM_PREC_FAST : NNLM_PREC_EXACT;
+    const int p = opt ? opt->precision : NNLM_PREC_AUTO;
+    if (p == NNLM_PREC_AUTO) return factorisation ? NNLM_PREC_AUTO : NNLM_PREC_EXACT;
     return p;
 }
 
@@ -508,6 +509,24 @@ int nnlm_cross(const double* Wt, const double* A, int32_t k, int64_t n, int64_t 
         eng.set_factors_t(Wt, H0.data());
         eng.cross_only(Q);
         fill_stats(stats, eng, launches0);
+        return NNLM_OK;
+    });
+}
+
+// diagnostic entry: the NA-path corrections of every column through the tensor-core mask contraction (na_gram.cu)
+int nnlm_na_corrections(const double* Wt, const double* A, int32_t k, int64_t n, int64_t m, double* S, int64_t s_capacity,
+                        int64_t* width, const nnlm_options* opt, char* err, size_t errlen)
+{
+    return guarded(err, errlen, [&]() -> int {
+        NNLM_REQUIRE(Wt && A && S && width && k > 0 && n > 0 && m > 0, "nnlm_na_corrections: bad argument");
+        ScopedDevice sd(device_of(opt));
+        Engine eng(n, m, k, NNLM_SCD_MSE, NNLM_PREC_FAST, opt ? opt->device : -1, /*both_sides=*/false);
+        eng.set_missing_mode(1);
+        eng.upload_A(A);
+        std::vector<double> H0((size_t)k * m, 0.0);
+        eng.set_factors_t(Wt, H0.data());
+        NNLM_REQUIRE(s_capacity >= m * ((int64_t)(k * (k + 1) / 2 + k + 127) / 128 * 128), "nnlm_na_corrections: S is too small");
+        *width = eng.na_corrections(S);
         return NNLM_OK;
     });
 }

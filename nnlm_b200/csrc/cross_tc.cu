@@ -146,14 +146,17 @@ __host__ __device__ inline int64_t first_cta_of_unit(int64_t u, int64_t U, int64
     return c;
 }
 
-template <int NP, int STAGES>
+// MODE 0: the three-product hi/lo scheme above. MODE 1: ONE product per k-step from the `hi` planes only, for operands that
+// are small integers stored in fp16 (the 0/1 missing mask and 11-bit fixed-point slices of the NA path, na_gram.cu): every
+// product and every fp32 partial sum below 2^24 is exact, so the result is exact up to the slicing.
+template <int NP, int STAGES, int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
            const __grid_constant__ CUtensorMap mapF_hi, const __grid_constant__ CUtensorMap mapF_lo, const CrossParams p)
 {
     constexpr int A_BYTES = BM * BK * 2;                   // 16 KB per plane per stage
     constexpr int F_BYTES = NP * BK * 2;
-    constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * F_BYTES;
+    constexpr int STAGE_BYTES = MODE == 0 ? 2 * A_BYTES + 2 * F_BYTES : A_BYTES + F_BYTES;
     constexpr int CPT = NP / 2;                            // accumulator columns per epilogue thread
     constexpr uint32_t TMEM_COLS = (4 * NP <= 128) ? 128 : (4 * NP <= 256 ? 256 : 512);
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // f16 x f16 -> f32, K-major
@@ -197,10 +200,15 @@ k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ 
                 uint8_t* sa = tiles + stage * STAGE_BYTES;
                 mbar_expect_tx(&full[stage], STAGE_BYTES);
                 const int c0 = (int)(kb * BK), c1 = (int)(tile * BM);
-                tma_load_2d(sa, &mapA_hi, &full[stage], c0, c1);
-                tma_load_2d(sa + A_BYTES, &mapA_lo, &full[stage], c0, c1);
-                tma_load_2d(sa + 2 * A_BYTES, &mapF_hi, &full[stage], c0, 0);
-                tma_load_2d(sa + 2 * A_BYTES + F_BYTES, &mapF_lo, &full[stage], c0, 0);
+                if (MODE == 0) {
+                    tma_load_2d(sa, &mapA_hi, &full[stage], c0, c1);
+                    tma_load_2d(sa + A_BYTES, &mapA_lo, &full[stage], c0, c1);
+                    tma_load_2d(sa + 2 * A_BYTES, &mapF_hi, &full[stage], c0, 0);
+                    tma_load_2d(sa + 2 * A_BYTES + F_BYTES, &mapF_lo, &full[stage], c0, 0);
+                } else {
+                    tma_load_2d(sa, &mapA_hi, &full[stage], c0, c1);
+                    tma_load_2d(sa + A_BYTES, &mapF_hi, &full[stage], c0, 0);
+                }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -225,14 +233,16 @@ k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ 
                         tc_fence_after();
                         const uint32_t sa = smem_u32(tiles + stage * STAGE_BYTES);
                         const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_BYTES);
-                        const uint64_t f_hi = make_desc(sa + 2 * A_BYTES), f_lo = make_desc(sa + 2 * A_BYTES + F_BYTES);
+                        const uint64_t f_hi = make_desc(sa + (MODE == 0 ? 2 * A_BYTES : A_BYTES)), f_lo = make_desc(sa + 2 * A_BYTES + F_BYTES);
 #pragma unroll
                         for (int ks = 0; ks < BK / 16; ks++) {
                             const uint64_t adv = (uint64_t)((ks * 32) >> 4);     // 16 fp16 = 32 bytes along K
                             const uint32_t acc = (first && ks == 0) ? 0u : 1u;
                             umma_f16(d0, a_hi + adv, f_hi + adv, IDESC, acc);    // hi*hi
-                            umma_f16(d1, a_hi + adv, f_lo + adv, IDESC, acc);    // hi*lo
-                            umma_f16(d1, a_lo + adv, f_hi + adv, IDESC, 1u);     // lo*hi
+                            if (MODE == 0) {
+                                umma_f16(d1, a_hi + adv, f_lo + adv, IDESC, acc);    // hi*lo
+                                umma_f16(d1, a_lo + adv, f_hi + adv, IDESC, 1u);     // lo*hi
+                            }
                         }
                         first = false;
                         tc_commit(&empty[stage]);               // frees the smem stage when these MMAs retire
@@ -269,7 +279,7 @@ k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ 
                 for (int ch = 0; ch < CPT / CH; ch++) {
                     uint32_t r0[CH], r1[CH];
                     TmemLd<CH>::ld(t0 + ch * CH, r0);
-                    TmemLd<CH>::ld(t0 + NP + ch * CH, r1);
+                    if (MODE == 0) TmemLd<CH>::ld(t0 + NP + ch * CH, r1);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (ch == CPT / CH - 1) {
                         tc_fence_before();
@@ -278,7 +288,8 @@ k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ 
                     }
 #pragma unroll
                     for (int c = 0; c < CH; c++)
-                        acc[ch * CH + c] += (double)__uint_as_float(r0[c]) + (double)__uint_as_float(r1[c]) * LO_UNSCALE;
+                        acc[ch * CH + c] += MODE == 0 ? (double)__uint_as_float(r0[c]) + (double)__uint_as_float(r1[c]) * LO_UNSCALE
+                                                      : (double)__uint_as_float(r0[c]);
                 }
                 u = chunk_end;
                 chunk++;
@@ -292,7 +303,7 @@ k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ 
 #pragma unroll
                 for (int c = 0; c < CPT; c++) {
                     const int a = half * CPT + c;
-                    if (a < p.k) out[a] = fma(cj, p.fsum[a], acc[c] * p.unscale[a]);
+                    if (a < p.k) out[a] = MODE == 0 ? fma(cj, p.fsum[a], acc[c] * p.unscale[a]) : acc[c] * p.unscale[a];
                 }
             }
         }
@@ -513,21 +524,22 @@ int sm_count()
     return n;
 }
 
-template <int NP, int STAGES>
+template <int NP, int STAGES, int MODE>
 void launch_np(const CrossPlan& plan, const __half* a_hi, const __half* a_lo, const __half* f_hi, const __half* f_lo,
-               const double* unscale, const double* center, const double* fsum, double* Qp, cudaStream_t st)
+               const double* unscale, const double* center, const double* fsum, double* Qp, int drain, cudaStream_t st)
 {
-    constexpr size_t smem = (size_t)STAGES * (2 * BM * BK * 2 + 2 * NP * BK * 2) + 1024 /*alignment slack*/ + 256;
-    auto kern = k_cross_tc<NP, STAGES>;
+    constexpr size_t stage = MODE == 0 ? (2 * BM * BK * 2 + 2 * NP * BK * 2) : (BM * BK * 2 + NP * BK * 2);
+    constexpr size_t smem = (size_t)STAGES * stage + 1024 /*alignment slack*/ + 256;
+    auto kern = k_cross_tc<NP, STAGES, MODE>;
     NNLM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const CUtensorMap mA_hi = make_map(a_hi, plan.len, plan.ncol, plan.ld_a, BM);
-    const CUtensorMap mA_lo = make_map(a_lo, plan.len, plan.ncol, plan.ld_a, BM);
+    const CUtensorMap mA_lo = MODE == 0 ? make_map(a_lo, plan.len, plan.ncol, plan.ld_a, BM) : mA_hi;
     const CUtensorMap mF_hi = make_map(f_hi, plan.len, NP, plan.ld_f, NP);
-    const CUtensorMap mF_lo = make_map(f_lo, plan.len, NP, plan.ld_f, NP);
+    const CUtensorMap mF_lo = MODE == 0 ? make_map(f_lo, plan.len, NP, plan.ld_f, NP) : mF_hi;
     CrossParams p;
     p.ncol = plan.ncol; p.kblocks = plan.kblocks; p.units = plan.units; p.k = plan.k; p.Qp = Qp; p.unscale = unscale;
     static const int drain_env = [] { const char* e = getenv("NNLM_TC_DRAIN"); return e ? atoi(e) : 0; }();
-    p.drain = drain_env > 0 ? drain_env : (NP >= 128 ? DRAIN_LARGE : DRAIN_SMALL);
+    p.drain = drain > 0 ? drain : (drain_env > 0 ? drain_env : (NP >= 128 ? DRAIN_LARGE : DRAIN_SMALL));
     p.center = center; p.fsum = fsum;
     NNLM_CUDA_CHECK(cudaMemsetAsync(Qp, 0, sizeof(double) * (size_t)plan.slots * plan.ncol * plan.k, st));
     kern<<<plan.grid, THREADS, smem, st>>>(mA_hi, mA_lo, mF_hi, mF_lo, p);
@@ -566,9 +578,18 @@ void launch_cross_tc(const CrossPlan& plan, const __half* a_hi, const __half* a_
                      const double* unscale, const double* center, const double* fsum, double* Qp, cudaStream_t st)
 {
     NNLM_REQUIRE(cross_tc_supported(plan.k), "tensor-core cross-product supports rank k <= 128");
-    if (plan.np == 32)      launch_np<32, 5>(plan, a_hi, a_lo, f_hi, f_lo, unscale, center, fsum, Qp, st);
-    else if (plan.np == 64) launch_np<64, 4>(plan, a_hi, a_lo, f_hi, f_lo, unscale, center, fsum, Qp, st);
-    else                    launch_np<128, 3>(plan, a_hi, a_lo, f_hi, f_lo, unscale, center, fsum, Qp, st);
+    if (plan.np == 32)      launch_np<32, 5, 0>(plan, a_hi, a_lo, f_hi, f_lo, unscale, center, fsum, Qp, 0, st);
+    else if (plan.np == 64) launch_np<64, 4, 0>(plan, a_hi, a_lo, f_hi, f_lo, unscale, center, fsum, Qp, 0, st);
+    else                    launch_np<128, 3, 0>(plan, a_hi, a_lo, f_hi, f_lo, unscale, center, fsum, Qp, 0, st);
+}
+
+// Exact contraction of two integer-valued fp16 planes (MODE 1): Qp[slot][ncol][128] = unscale[a] * sum_i f[a,i] * a[i,j].
+// |f| <= 2047 and a in {0, 1}: a TMEM partial sum over 64 k-blocks (4096 indices) stays below 2^24, hence exact in fp32.
+void launch_cross_tc_exact(const CrossPlan& plan, const __half* a_plane, const __half* f_plane, const double* unscale, double* Qp,
+                           cudaStream_t st)
+{
+    NNLM_REQUIRE(plan.np == 128, "the exact integer contraction runs on 128-row factor tiles");
+    launch_np<128, 6, 1>(plan, a_plane, nullptr, f_plane, nullptr, unscale, nullptr, nullptr, Qp, 64, st);
 }
 
 void launch_means(const double* A, int64_t len, int64_t ncol, double* colmean, double* rowmean, cudaStream_t st)
@@ -604,6 +625,14 @@ void launch_split_matrix(const double* A, int64_t len, int64_t ncol, const doubl
     NNLM_REQUIRE(ceil_div(ncol, 32) <= 65535, "too many columns for the plane conversion grid");
     dim3 grid((unsigned)ceil_div(len, 32), (unsigned)ceil_div(ncol, 32));
     k_split_matrix<<<grid, 256, 0, st>>>(A, len, ncol, sA, colmean, rowmean, a_hi, a_lo, ld_a, t_hi, t_lo, ld_t);
+    NNLM_LAUNCHED();
+}
+
+void launch_rowmax(const double* F, int k, int64_t len, unsigned long long* rowmax, cudaStream_t st)
+{
+    NNLM_CUDA_CHECK(cudaMemsetAsync(rowmax, 0, sizeof(unsigned long long) * k, st));
+    const int64_t total = (int64_t)k * len;
+    k_rowmax<<<(int)std::min<int64_t>(ceil_div(total, 256 * 8), 148 * 4), 256, sizeof(unsigned long long) * k, st>>>(F, k, len, rowmax);
     NNLM_LAUNCHED();
 }
 

@@ -173,7 +173,35 @@ void Engine::ingest_shards(const double* dAcol, const double* dArow)
     sum_sq_a_ = host_small_.p[2];
     q_valid_ = false;
     // pass 2: the resident copies, in the storage the precision policy selects (include/nnlm_b200.h)
-    if (precision_req_ == NNLM_PREC_FAST && method_ <= 2 && cross_tc_supported(k_) && !use_missing_path())
+    if (precision_req_ == NNLM_PREC_AUTO) {
+        // small problems gain nothing from reduced storage; large dense square-loss problems take the tensor-core planes
+        // unless the data is so heavy-tailed that single entries rival whole column sums: the fp32 TMEM accumulator then
+        // loses the small products added after a spike (measured 5e-6 of sum|F||A| with one entry at 1e4 x rms,
+        // tests/test_gpu_scale_parity.py). Entries up to rms * min(n, m) / 16 keep that loss below ~1e-7.
+        const bool large = (double)n_ * (double)m_ >= 4.0e6;
+        int choice = NNLM_PREC_EXACT;
+        if (large) {
+            choice = NNLM_PREC_FAST;
+            if (method_ <= 2 && cross_tc_supported(k_) && !use_missing_path()) {
+                unsigned long long* mx = reinterpret_cast<unsigned long long*>(small_.p + 8);
+                launch_absmax(dAcol, (int64_t)cnt_c, mx, st_);
+                if (comm_) comm_->allreduce_max_u64(mx, 1, st_);
+                NNLM_CUDA_CHECK(cudaMemcpyAsync(host_small_.p + 8, mx, sizeof(double), cudaMemcpyDeviceToHost, st_));
+                sync();
+                d2h_bytes += sizeof(double);
+                const double amax = host_small_.p[8];          // the bit pattern of max |A| IS that double
+                const double finite = (double)n_ * (double)m_ - (double)n_missing_;
+                const double rms = finite > 0 ? std::sqrt(sum_sq_a_ / finite) : 0.0;
+                if (amax > rms * (double)std::min(n_, m_) / 16.0) choice = NNLM_PREC_EXACT;
+            }
+        }
+        precision_req_ = choice;
+        storage_ = choice == NNLM_PREC_FAST ? Storage::F32 : Storage::F64;
+    }
+    // fast square-loss path: fp16 planes for the tensor-core cross-product; with missing entries the planes hold zero there
+    // (= the column mean after centring) and the NA corrections come from the mask contraction of na_gram.cu
+    if (precision_req_ == NNLM_PREC_FAST && method_ <= 2 && cross_tc_supported(k_)
+        && (!use_missing_path() || std::getenv("NNLM_NA_FP64") == nullptr))
         storage_ = Storage::F16X2;
     if (storage_ == Storage::F64) {
         if (dAcol != A64_.p) {
@@ -218,6 +246,29 @@ void Engine::ingest_shards(const double* dAcol, const double* dArow)
             NNLM_CUDA_CHECK(cudaMemsetAsync(t_lo_.p, 0, t_lo_.bytes(), st_));
             launch_means(dArow, nr_, m_, nullptr, rowmean_.p, st_);
             launch_split_matrix(dArow, nr_, m_, scale_a_.p, nullptr, rowmean_.p, nullptr, nullptr, 0, t_hi_.p, t_lo_.p, ld_m, st_);
+        }
+        if (use_missing_path()) {
+            // the missing indicator as fp16 0/1 planes, and the scratch of the mask contraction
+            const int64_t pt = na_packed_width(k_);
+            size_t q2 = 0, sN = 0;
+            if (mc_ > 0) {
+                mk_.alloc((size_t)ld_n * mc_);
+                NNLM_CUDA_CHECK(cudaMemsetAsync(mk_.p, 0, mk_.bytes(), st_));
+                launch_mask_planes<double>(dAcol, n_, mc_, mk_.p, ld_n, nullptr, 0, st_);
+                plan_na_h_ = cross_tc_plan(NA_TILE, n_, mc_);
+                q2 = (size_t)plan_na_h_.slots * mc_ * NA_TILE; sN = (size_t)mc_ * pt;
+            }
+            if (both_sides_ && nr_ > 0) {
+                mkt_.alloc((size_t)ld_m * nr_);
+                NNLM_CUDA_CHECK(cudaMemsetAsync(mkt_.p, 0, mkt_.bytes(), st_));
+                launch_mask_planes<double>(dArow, nr_, m_, nullptr, 0, mkt_.p, ld_m, st_);
+                plan_na_w_ = cross_tc_plan(NA_TILE, m_, nr_);
+                q2 = std::max(q2, (size_t)plan_na_w_.slots * nr_ * NA_TILE); sN = std::max(sN, (size_t)nr_ * pt);
+            }
+            zplanes_.alloc((size_t)NA_SLICES * NA_TILE * ld_f);
+            zunscale_.alloc((size_t)NA_SLICES * NA_TILE);
+            Qp2_.alloc(q2);
+            S_.alloc(sN);
         }
     }
     sync();
@@ -374,7 +425,8 @@ void Engine::run_half_t(const Half& h)
 void Engine::run_half_tc(const Half& h)
 {
     const CrossPlan& plan = h.w_side ? plan_w_ : plan_h_;
-    fork_gram(h, false);
+    const bool missing = use_missing_path();
+    fork_gram(h, missing);
     if (h.ncol > 0) {
         timer.begin(KernelTimer::GRAM, st_);
         launch_split_factor(h.Y, k_, h.len, plan.ld_f, plan.np, scale_a_.p, rowmax_.p, fscales_.p, unscale_.p, f_hi_.p, f_lo_.p, st_);
@@ -385,7 +437,23 @@ void Engine::run_half_tc(const Half& h)
                         h.w_side ? rowmean_.p : colmean_.p, sumY_.p, Qp_.p, st_);
         timer.end(st_);
     }
-    solve_dense_ls(h, plan.slots);
+    if (!missing) { solve_dense_ls(h, plan.slots); return; }
+    // NA path (src/update_with_missing.cpp:58-139): the cross-product above read missing entries as the column mean; the mask
+    // contraction delivers, per column, the Gram of the missing rows and their row sums, and the solver assembles
+    // G_j = G - S_j and q_j = Q_j - mean_j * (masked row sums) on the fly
+    if (h.ncol > 0) {
+        const CrossPlan& pna = h.w_side ? plan_na_w_ : plan_na_h_;
+        timer.begin(KernelTimer::GRAM, st_);
+        launch_na_gram_tc(pna, h.Y, k_, h.w_side ? mkt_.p : mk_.p, rowmax_.p, zplanes_.p, zunscale_.p, Qp2_.p, S_.p, st_);
+        timer.end(st_);
+    }
+    join_gram();
+    timer.begin(KernelTimer::SOLVE, st_);
+    if (h.ncol > 0)
+        launch_solve_ls_missing_packed(method_, h.X, Graw_.p, S_.p, na_packed_width(k_), Qp_.p, plan.slots,
+                                       h.w_side ? rowmean_.p : colmean_.p, h.mask, k_, h.ncol, h.pen, inner_max_iter_,
+                                       inner_rel_tol_, sweeps_.p, st_);
+    timer.end(st_);
 }
 
 void Engine::run_half(const Half& h)
@@ -456,6 +524,33 @@ void Engine::cross_only(double* Q_host)
         for (int sp = 0; sp < splits; sp++) s += tmp[(size_t)sp * per + e];
         Q_host[e] = s;
     }
+    if (storage_ == Storage::F16X2 && use_missing_path()) {
+        // the planes read a missing entry as its column mean: take mean_j * (row sums of the factor over the missing rows) out
+        // again, exactly as the NA solver does (the masked product of src/update_with_missing.cpp:91)
+        const int64_t pt = na_packed_width(k_);
+        launch_na_gram_tc(plan_na_h_, Wt_.p, k_, mk_.p, rowmax_.p, zplanes_.p, zunscale_.p, Qp2_.p, S_.p, st_);
+        std::vector<double> S((size_t)m_ * pt), cm(m_);
+        NNLM_CUDA_CHECK(cudaMemcpyAsync(S.data(), S_.p, S.size() * sizeof(double), cudaMemcpyDeviceToHost, st_));
+        NNLM_CUDA_CHECK(cudaMemcpyAsync(cm.data(), colmean_.p, cm.size() * sizeof(double), cudaMemcpyDeviceToHost, st_));
+        sync();
+        d2h_bytes += (S.size() + cm.size()) * sizeof(double);
+        const int kk2 = k_ * (k_ + 1) / 2;
+        for (int64_t j = 0; j < m_; j++)
+            for (int a = 0; a < k_; a++) Q_host[a + (size_t)k_ * j] -= cm[j] * S[(size_t)j * pt + kk2 + a];
+    }
+}
+
+int64_t Engine::na_corrections(double* S_host)
+{
+    DeviceGuard g(device_);
+    NNLM_REQUIRE(comm_ == nullptr && storage_ == Storage::F16X2 && use_missing_path(),
+                 "na_corrections needs the fast-precision NA path on one GPU");
+    const int64_t pt = na_packed_width(k_);
+    launch_na_gram_tc(plan_na_h_, Wt_.p, k_, mk_.p, rowmax_.p, zplanes_.p, zunscale_.p, Qp2_.p, S_.p, st_);
+    NNLM_CUDA_CHECK(cudaMemcpyAsync(S_host, S_.p, sizeof(double) * (size_t)m_ * pt, cudaMemcpyDeviceToHost, st_));
+    sync();
+    d2h_bytes += sizeof(double) * (size_t)m_ * pt;
+    return pt;
 }
 
 void Engine::errors(ErrorTerms* out, bool want_kl)

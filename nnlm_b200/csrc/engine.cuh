@@ -98,6 +98,9 @@ public:
     double sum_sq_A() const { return sum_sq_a_; }
     // diagnostic: Q = Wt * A (k x m, missing entries of A read as zero) through the cross-product path of the current storage
     void cross_only(double* Q_host);
+    // diagnostic: the per-column corrections of the NA path through the tensor-core mask contraction (na_gram.cu):
+    // S_host[j * width + pair(a,b)] = sum_{i missing in column j} W[i,a] W[i,b], then the k masked row sums; returns width
+    int64_t na_corrections(double* S_host);
     uint64_t take_sweeps();                       // read and reset the global total_raw_iter (synchronises)
     void sync();
 
@@ -153,6 +156,11 @@ private:
     // fp16 hi/lo planes for the tensor-core cross-product (cross_tc.cu): column copy [mc][ld(n)], row copy [nr][ld(m)],
     // factor [np][ld]
     DevBuf<__half> a_hi_, a_lo_, t_hi_, t_lo_, f_hi_, f_lo_;
+    // NA path on the tensor cores (na_gram.cu): 0/1 planes of the missing indicator in both orientations, the fixed-point
+    // slices of one tile of the Khatri-Rao product, and the packed per-column corrections
+    DevBuf<__half> mk_, mkt_, zplanes_;
+    DevBuf<double> zunscale_, Qp2_, S_;
+    CrossPlan plan_na_h_, plan_na_w_;
     DevBuf<double> scale_a_, fscales_, unscale_, colmean_, rowmean_;
     DevBuf<unsigned long long> rowmax_;
     CrossPlan plan_h_, plan_w_;

@@ -89,6 +89,11 @@ void launch_split_matrix(const double* A, int64_t len, int64_t ncol, const doubl
 // F (k x len col-major fp64) -> planes [np][ld] with per-row power-of-two scales; unscale[a] = 1/(sA*scale[a])
 void launch_split_factor(const double* F, int k, int64_t len, int64_t ld, int np, const double* sA, unsigned long long* rowmax,
                          double* scales, double* unscale, __half* hi, __half* lo, cudaStream_t st);
+// rowmax[a] = bit pattern of max_i |F[a,i]| (zeroed here)
+void launch_rowmax(const double* F, int k, int64_t len, unsigned long long* rowmax, cudaStream_t st);
+// exact contraction of integer-valued fp16 planes (cross_tc.cu MODE 1); plan from cross_tc_plan(128, len, ncol)
+void launch_cross_tc_exact(const CrossPlan& plan, const __half* a_plane, const __half* f_plane, const double* unscale, double* Qp,
+                           cudaStream_t st);
 
 // ---- solve_ls.cu: K3/K4/K5 — warp-per-column sequential coordinate descent / Lee multiplicative, square loss ----
 // X (k x ncol) in/out; G regularised Gram (k x k); Qp split-K partials of Wt*A (splits x k x ncol); mask k x ncol bytes or null;
@@ -110,6 +115,25 @@ template <typename TA>
 void launch_solve_ls_missing(int method, double* X, const double* Y, const TA* A, const double* Gfull, const double* Qp,
                              int splits, const uint8_t* mask, int k, int64_t len, int64_t ncol, const double* pen,
                              unsigned max_iter, double rel_tol, unsigned long long* sweeps, cudaStream_t st);
+
+// ---- na_gram.cu: K9 on the tensor cores (fast-precision NA path) ----
+constexpr int NA_SLICES = 4;     // 11-bit fixed-point slices per column of the Khatri-Rao product
+constexpr int NA_TILE = 128;     // Z columns per contraction (rows of one factor-plane tile)
+int     na_pair_count(int k);    // k (k + 1) / 2 pairs (a >= b) + k linear columns
+int64_t na_packed_width(int k);  // na_pair_count rounded up to a multiple of NA_TILE: row pitch of the packed result
+// fp16 0/1 planes of the missing indicator of A (len x ncol, column-major): a_plane[j][i] and t_plane[i][j]; either may be null
+template <typename TA>
+void launch_mask_planes(const TA* A, int64_t len, int64_t ncol, __half* a_plane, int64_t ld_a, __half* t_plane, int64_t ld_t,
+                        cudaStream_t st);
+// S[j][pair(a,b)] = sum_{i missing in column j} Y[a,i] Y[b,i] (a >= b, pair = a (a + 1) / 2 + b), S[j][k(k+1)/2 + a] =
+// sum_{i missing} Y[a,i]; exact up to a 2^-44 truncation of each product against its column bound. plan = cross_tc_plan(128, len, ncol).
+void launch_na_gram_tc(const CrossPlan& plan, const double* Y, int k, const __half* mask_plane, unsigned long long* rowmax,
+                       __half* zplanes, double* zunscale, double* Qp, double* S, cudaStream_t st);
+// the NA-path solve from the packed corrections: G_j = Gfull - S_j (+ regularisation), q_j = sum of the Qp slots
+// (- center[j] * masked row sums when center != nullptr: the cross-product was formed on centred planes with missing = 0)
+void launch_solve_ls_missing_packed(int method, double* X, const double* Gfull, const double* S, int64_t pt, const double* Qp,
+                                    int splits, const double* center, const uint8_t* mask, int k, int64_t ncol, const double* pen,
+                                    unsigned max_iter, double rel_tol, unsigned long long* sweeps, cudaStream_t st);
 
 // ---- solve_kl.cu: K7/K8, KL loss, dense and NA (src/base_algorithms.cpp:71-151, update_with_missing.cpp:119-131) ----
 // Yr is the ROW-major copy of the fixed factor: Yr[c*len + i] = Y[c + k*i]; sumY = rowSums(Y) (launch_rowsum).

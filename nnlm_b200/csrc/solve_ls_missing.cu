@@ -224,6 +224,83 @@ k_solve_batch(double* __restrict__ X, const double* __restrict__ Gin, const doub
     if (lane == 0 && my_sweeps) atomicAdd(sweeps, my_sweeps);
 }
 
+// Kernel B': as kernel B, with the per-column Gram assembled on the fly from the shared raw Gram and the packed tensor-core
+// corrections of na_gram.cu: G_j[a,b] = Gfull[a,b] - S[j][pair(max, min)] + regularisation (src/update_with_missing.cpp:98-103).
+template <int RPL, int METHOD>
+__global__ void __launch_bounds__(256)
+k_solve_batch_packed(double* __restrict__ X, const double* __restrict__ Gfull, const double* __restrict__ S, int64_t pt,
+                     const double* __restrict__ Qp, int splits, const double* __restrict__ center, const uint8_t* __restrict__ mask,
+                     int k, int64_t ncol, double p0, double p1, double l1, unsigned max_iter, double rel_tol,
+                     unsigned long long* __restrict__ sweeps)
+{
+    constexpr int KR = 32 * RPL;
+    extern __shared__ __align__(32) double smd[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    double* gs = smd + (size_t)warp * KR * KR;      // [KR][KR] column-major, rows / columns >= k zero
+    unsigned long long my_sweeps = 0;
+    const int kk2 = k * (k + 1) / 2;
+    for (int e = lane; e < KR * KR; e += 32) gs[e] = 0.0;
+    for (int64_t col = (int64_t)blockIdx.x * wpc + warp; col < ncol; col += (int64_t)gridDim.x * wpc) {
+        const uint8_t* mcol = mask ? mask + (int64_t)k * col : nullptr;
+        if (mcol) {                                          // src/update_with_missing.cpp:77-78
+            int nm = 0;
+            for (int c = 0; c < k; c++) nm += mcol[c] != 0;
+            if (nm == k) continue;
+        }
+        __syncwarp();
+        const double* Sj = S + pt * col;
+        for (int e = lane; e < k * k; e += 32) {
+            const int a = e % k, b = e / k;
+            const int hi = a > b ? a : b, lo = a > b ? b : a;
+            double g = Gfull[e] - Sj[hi * (hi + 1) / 2 + lo];
+            if (p0 != p1 && a == b) g += p0 - p1;
+            if (p1 != 0.0) g += p1;
+            if (a == b) g += TINY_NUM;
+            gs[a + KR * b] = g;
+        }
+        __syncwarp();
+        double h[RPL], q[RPL];
+        unsigned mk[RPL];
+        const double cj = center ? center[col] : 0.0;
+#pragma unroll
+        for (int s = 0; s < RPL; s++) {
+            const int r = lane + 32 * s;
+            const bool valid = r < k;
+            h[s] = valid ? X[r + (int64_t)k * col] : 0.0;
+            double a = 0.0;
+            if (valid) {
+                for (int sp = 0; sp < splits; sp++) a += Qp[((int64_t)sp * ncol + col) * k + r];
+                if (center) a = fma(-cj, Sj[kk2 + r], a);   // the planes held A - c_j with missing = 0: remove c_j * (masked row sum)
+            }
+            q[s] = a;
+            const bool mb = valid && mcol != nullptr && mcol[r] != 0;
+            mk[s] = __ballot_sync(0xffffffffu, mb);
+        }
+        my_sweeps += warp_solve_ls<RPL, METHOD>(h, q, mk, gs, k, l1, max_iter, rel_tol);
+#pragma unroll
+        for (int s = 0; s < RPL; s++) {
+            const int r = lane + 32 * s;
+            if (r < k) X[r + (int64_t)k * col] = h[s];
+        }
+    }
+    if (lane == 0 && my_sweeps) atomicAdd(sweeps, my_sweeps);
+}
+
+template <int RPL>
+void launch_packed_rpl(int method, double* X, const double* Gfull, const double* S, int64_t pt, const double* Qp, int splits,
+                       const double* center, const uint8_t* mask, int k, int64_t ncol, const double* pen, unsigned max_iter,
+                       double rel_tol, unsigned long long* sweeps, cudaStream_t st)
+{
+    constexpr int KR = 32 * RPL;
+    const int wpc = std::max(1, std::min(7, (int)(220 * 1024 / (sizeof(double) * KR * KR))));
+    const size_t smem = sizeof(double) * (size_t)wpc * KR * KR;
+    auto kb = method == 1 ? k_solve_batch_packed<RPL, 1> : k_solve_batch_packed<RPL, 2>;
+    NNLM_CUDA_CHECK(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(ncol, wpc), 148 * 4));
+    kb<<<grid, 32 * wpc, smem, st>>>(X, Gfull, S, pt, Qp, splits, center, mask, k, ncol, pen[0], pen[1], pen[2], max_iter, rel_tol, sweeps);
+    NNLM_LAUNCHED();
+}
+
 template <int RPL, typename TA>
 void launch_rpl(int method, double* X, const double* Y, const TA* A, const double* Gfull, const double* Qp, int splits,
                 const uint8_t* mask, int k, int64_t len, int64_t ncol, const double* pen, unsigned max_iter, double rel_tol,
@@ -256,6 +333,21 @@ void launch_rpl(int method, double* X, const double* Y, const TA* A, const doubl
 }
 
 }  // namespace
+
+void launch_solve_ls_missing_packed(int method, double* X, const double* Gfull, const double* S, int64_t pt, const double* Qp,
+                                    int splits, const double* center, const uint8_t* mask, int k, int64_t ncol, const double* pen,
+                                    unsigned max_iter, double rel_tol, unsigned long long* sweeps, cudaStream_t st)
+{
+    NNLM_REQUIRE(method == 1 || method == 2, "solve_ls_missing handles methods 1 and 2");
+    NNLM_REQUIRE(k >= 1 && k <= 128, "rank k must be in [1, 128]");
+    if (ncol <= 0) return;
+    switch ((k + 31) / 32) {
+        case 1: launch_packed_rpl<1>(method, X, Gfull, S, pt, Qp, splits, center, mask, k, ncol, pen, max_iter, rel_tol, sweeps, st); break;
+        case 2: launch_packed_rpl<2>(method, X, Gfull, S, pt, Qp, splits, center, mask, k, ncol, pen, max_iter, rel_tol, sweeps, st); break;
+        case 3: launch_packed_rpl<3>(method, X, Gfull, S, pt, Qp, splits, center, mask, k, ncol, pen, max_iter, rel_tol, sweeps, st); break;
+        default: launch_packed_rpl<4>(method, X, Gfull, S, pt, Qp, splits, center, mask, k, ncol, pen, max_iter, rel_tol, sweeps, st); break;
+    }
+}
 
 template <typename TA>
 void launch_solve_ls_missing(int method, double* X, const double* Y, const TA* A, const double* Gfull, const double* Qp,
