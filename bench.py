@@ -243,6 +243,8 @@ def main():
     comm = None
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # keeps NCCL's banner off stdout: one JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         comm = shard.comm_from_torch(local_rank)
@@ -325,22 +327,39 @@ def main():
                     "algorithmic_fma_per_launch": fma / max(st["solve_launches"], 1), "ms_per_launch": solve_ms,
                     "peak_source": fp64_src}
     elif wl["method"] >= 3:
-        # KL updates: per half n*m*k entries x inner sweeps, each one division + two FMA (src/base_algorithms.cpp:141-143);
-        # a correctly rounded fp64 division is ~9 fp64-pipe instructions, so the pipe slots are counted as 11 per entry
+        # KL updates (src/base_algorithms.cpp:119-151): per half n*m*k entries x inner sweeps, each ONE reciprocal on the MUFU
+        # (special-function) pipe + 4 fp32 instructions; the kernel keeps wh / A on chip, so neither HBM nor L2 binds. The
+        # roofline is the MUFU rate: 16 results / clk / SM.
         ent = 2.0 * n * m * k * wl["inner"] / world
         t = st["solve_ms"] / args.steps * 1e-3
-        tfma = 11.0 * ent / t / 1e12 if t > 0 else 0.0
-        roofline = {"bound": "fp64", "achieved": tfma, "peak": fp64_peak, "unit": "TFMA-slots/s", "frac": tfma / fp64_peak, "traffic": None,
-                    "kernel": "k_solve_kl (both halves), per GPU", "entries_per_step": ent,
-                    "slots_per_entry": "1 fp64 division (9 pipe slots) + 2 FMA", "ms_per_launch": solve_ms, "peak_source": fp64_src}
+        mufu_peak = 16.0 * 148 * sm_mhz * 1e6 / 1e12
+        ach = ent / t / 1e12 if t > 0 else 0.0
+        roofline = {"bound": "mufu", "achieved": ach, "peak": mufu_peak, "unit": "T reciprocals/s", "frac": ach / mufu_peak, "traffic": None,
+                    "kernel": "k_solve_kl_fast (both halves: cluster kernel, wh in registers, A in shared memory), per GPU",
+                    "entries_per_step": ent, "ms_per_launch": solve_ms,
+                    "peak_source": "16 MUFU results/clk/SM x 148 SMs x sampled SM clock (B300_MICROARCH.md SFU rate; sm_100a has the 1x rate)"}
     else:
-        # NA path: per-column Gram by complement, nnz_missing * k(k+1)/2 FMA per half (symmetric minimum)
-        fma = 2.0 * wl["na"] * n * m * k * (k + 1) / 2 / world
-        t = st["solve_ms"] / args.steps * 1e-3
-        tfma = fma / t / 1e12 if t > 0 else 0.0
-        roofline = {"bound": "fp64", "achieved": tfma, "peak": fp64_peak, "unit": "TFMA/s", "frac": tfma / fp64_peak, "traffic": None,
-                    "kernel": "k_gram_missing + k_solve_batch (per-column Gram by complement + SCD), per GPU",
-                    "algorithmic_fma_per_step": fma, "ms_per_launch": solve_ms, "peak_source": fp64_src}
+        # NA path: the per-column masked Grams as one tensor-core contraction (na_gram.cu): 2 halves x 2 n m (k(k+1)/2 + k)
+        # multiply-adds x 4 fixed-point slices, fp16 operands; the kernel re-streams the fp16 mask plane once per 128 Z columns
+        # and slice, so the HBM side is reported beside the tensor side.
+        P = k * (k + 1) // 2 + k
+        flops = 2.0 * 2.0 * n * m * P * 4 / world
+        t = st["gram_ms"] / args.steps * 1e-3
+        ach = flops / t / 1e12 if t > 0 else 0.0
+        tpeak, tsrc = 1664.9, "fallback (B200_PROFILING.md dense bf16/fp16)"
+        try:
+            d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            tpeak, tsrc = float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops burst; fp16 runs at the same rate)"
+        except Exception:
+            pass
+        launches_per_half = -(-P // 128) * 4
+        mask_bytes = 2.0 * launches_per_half * n * m * 2 / world
+        roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None,
+                    "kernel": "k_cross_tc<128,6,1> x %d launches per half (mask x Khatri-Rao slices) + k_z_slices + k_fold, per GPU" % launches_per_half,
+                    "algorithmic_flop_per_step": flops, "ms_per_step_in_these_kernels": t * 1e3, "peak_source": tsrc,
+                    "hbm_side": {"achieved": mask_bytes / t / 1e9 if t > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
+                                 "bytes_per_step": mask_bytes, "what": "fp16 mask plane streamed once per launch"},
+                    "solve_ms_per_step": st["solve_ms"] / args.steps}
     roofline["share_of_step"] = share
     if cross:
         roofline["cross"] = cross
@@ -371,8 +390,9 @@ def main():
     sess.close()
 
     dtype = "f64 solver state, " + ("f64 A" if s_bytes == 8 else
-                                    ("fp16 hi+lo planes of A (4 B/element), fp32 TMEM accumulate drained to f64" if (wl["method"] <= 2 and wl["na"] == 0.0)
-                                     else "f32 A (4 B/element), every product and sum in f64"))
+                                    ("fp16 hi+lo planes of A (4 B/element), fp32 TMEM accumulate drained to f64" if wl["method"] <= 2 and wl["na"] == 0.0
+                                     else "fp16 hi+lo planes of A + fp16 0/1 mask plane; per-column Grams from exact fixed-point fp16 slices on tcgen05" if wl["method"] <= 2
+                                     else "f32 A, f32 wh and ratios, sums / h / updates in f64"))
     line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": dtype, "data": "synthetic",

@@ -31,8 +31,11 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "tc_common.cuh"
 
 namespace nnlm {
+
+using namespace tc;
 
 namespace {
 
@@ -48,83 +51,6 @@ constexpr int DRAIN_SMALL = 4;    // NP = 32, 64: 256 contraction indices
 constexpr int DRAIN_LARGE = 2;    // NP = 128:    128 contraction indices
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 32 * (2 + EPI_WARPS);
-constexpr float LO_SCALE = 2048.0f;            // 2^11
-constexpr double LO_UNSCALE = 1.0 / 2048.0;
-
-// ---------------------------------------------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    const uint32_t addr = smem_u32(bar);
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc], fp16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-// K-major SWIZZLE_128B operand descriptor: 8-row groups 1024 bytes apart (SBO), version 1 (sm_100), layout type 2
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;                  // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;        // stride byte offset
-    d |= (uint64_t)1 << 46;                  // descriptor version
-    d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
-    return d;
-}
-
-template <int N> struct TmemLd;
-template <> struct TmemLd<16> {
-    __device__ static __forceinline__ void ld(uint32_t taddr, uint32_t (&r)[16]) {
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                     : "r"(taddr));
-    }
-};
-template <> struct TmemLd<32> {
-    __device__ static __forceinline__ void ld(uint32_t taddr, uint32_t (&r)[32]) {
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                     "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                       "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                     : "r"(taddr));
-    }
-};
 
 struct CrossParams {
     int64_t ncol;          // columns of A (rows of the UMMA M operand)
@@ -148,7 +74,9 @@ __host__ __device__ inline int64_t first_cta_of_unit(int64_t u, int64_t U, int64
 
 // MODE 0: the three-product hi/lo scheme above. MODE 1: ONE product per k-step from the `hi` planes only, for operands that
 // are small integers stored in fp16 (the 0/1 missing mask and 11-bit fixed-point slices of the NA path, na_gram.cu): every
-// product and every fp32 partial sum below 2^24 is exact, so the result is exact up to the slicing.
+// product and every fp32 partial sum below 2^24 is exact, so the result is exact up to the slicing. MODE 2: the same with
+// TWO factor planes per pass (two consecutive slices, 2^11 apart: f_hi, f_lo) against the one `hi` plane of A, combined
+// like MODE 0 in the epilogue — the mask plane is streamed once for two slices.
 template <int NP, int STAGES, int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
@@ -156,7 +84,7 @@ k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ 
 {
     constexpr int A_BYTES = BM * BK * 2;                   // 16 KB per plane per stage
     constexpr int F_BYTES = NP * BK * 2;
-    constexpr int STAGE_BYTES = MODE == 0 ? 2 * A_BYTES + 2 * F_BYTES : A_BYTES + F_BYTES;
+    constexpr int STAGE_BYTES = MODE == 0 ? 2 * A_BYTES + 2 * F_BYTES : (MODE == 1 ? A_BYTES + F_BYTES : A_BYTES + 2 * F_BYTES);
     constexpr int CPT = NP / 2;                            // accumulator columns per epilogue thread
     constexpr uint32_t TMEM_COLS = (4 * NP <= 128) ? 128 : (4 * NP <= 256 ? 256 : 512);
     constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);   // f16 x f16 -> f32, K-major
@@ -208,6 +136,7 @@ k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ 
                 } else {
                     tma_load_2d(sa, &mapA_hi, &full[stage], c0, c1);
                     tma_load_2d(sa + A_BYTES, &mapF_hi, &full[stage], c0, 0);
+                    if (MODE == 2) tma_load_2d(sa + A_BYTES + F_BYTES, &mapF_lo, &full[stage], c0, 0);
                 }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
@@ -233,16 +162,15 @@ k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ 
                         tc_fence_after();
                         const uint32_t sa = smem_u32(tiles + stage * STAGE_BYTES);
                         const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_BYTES);
-                        const uint64_t f_hi = make_desc(sa + (MODE == 0 ? 2 * A_BYTES : A_BYTES)), f_lo = make_desc(sa + 2 * A_BYTES + F_BYTES);
+                        const uint64_t f_hi = make_desc(sa + (MODE == 0 ? 2 * A_BYTES : A_BYTES));
+                        const uint64_t f_lo = make_desc(sa + (MODE == 0 ? 2 * A_BYTES + F_BYTES : A_BYTES + F_BYTES));
 #pragma unroll
                         for (int ks = 0; ks < BK / 16; ks++) {
                             const uint64_t adv = (uint64_t)((ks * 32) >> 4);     // 16 fp16 = 32 bytes along K
                             const uint32_t acc = (first && ks == 0) ? 0u : 1u;
                             umma_f16(d0, a_hi + adv, f_hi + adv, IDESC, acc);    // hi*hi
-                            if (MODE == 0) {
-                                umma_f16(d1, a_hi + adv, f_lo + adv, IDESC, acc);    // hi*lo
-                                umma_f16(d1, a_lo + adv, f_hi + adv, IDESC, 1u);     // lo*hi
-                            }
+                            if (MODE != 1) umma_f16(d1, a_hi + adv, f_lo + adv, IDESC, acc);    // hi*lo (MODE 2: the next slice)
+                            if (MODE == 0) umma_f16(d1, a_lo + adv, f_hi + adv, IDESC, 1u);      // lo*hi
                         }
                         first = false;
                         tc_commit(&empty[stage]);               // frees the smem stage when these MMAs retire
@@ -279,7 +207,7 @@ k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ 
                 for (int ch = 0; ch < CPT / CH; ch++) {
                     uint32_t r0[CH], r1[CH];
                     TmemLd<CH>::ld(t0 + ch * CH, r0);
-                    if (MODE == 0) TmemLd<CH>::ld(t0 + NP + ch * CH, r1);
+                    if (MODE != 1) TmemLd<CH>::ld(t0 + NP + ch * CH, r1);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     if (ch == CPT / CH - 1) {
                         tc_fence_before();
@@ -288,7 +216,7 @@ k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ 
                     }
 #pragma unroll
                     for (int c = 0; c < CH; c++)
-                        acc[ch * CH + c] += MODE == 0 ? (double)__uint_as_float(r0[c]) + (double)__uint_as_float(r1[c]) * LO_UNSCALE
+                        acc[ch * CH + c] += MODE != 1 ? (double)__uint_as_float(r0[c]) + (double)__uint_as_float(r1[c]) * LO_UNSCALE
                                                       : (double)__uint_as_float(r0[c]);
                 }
                 u = chunk_end;
@@ -332,16 +260,6 @@ __global__ void k_rowmax(const double* __restrict__ F, int k, int64_t len, unsig
     for (int a = threadIdx.x; a < k; a += blockDim.x) if (smx[a]) atomicMax(&rowmax[a], smx[a]);
 }
 
-// power-of-two scale that brings `maxabs` into [2^13, 2^14): fp16 keeps 11 significant bits there and the scaled
-// remainder (< 2^3 before the 2^11 lift) stays far from both overflow and the subnormal range
-__device__ __forceinline__ double pow2_scale(double maxabs)
-{
-    if (!(maxabs > 0.0)) return 1.0;
-    int e;
-    frexp(maxabs, &e);                 // maxabs = f * 2^e, f in [0.5, 1)
-    return ldexp(1.0, 14 - e);
-}
-
 // scales[a] = s_F[a]; unscale[a] = 1 / (s_A * s_F[a])
 __global__ void k_make_scales(const unsigned long long* __restrict__ rowmax, int k, int np, const double* __restrict__ sA,
                               double* __restrict__ scales, double* __restrict__ unscale)
@@ -351,14 +269,6 @@ __global__ void k_make_scales(const unsigned long long* __restrict__ rowmax, int
     const double s = (a < k) ? pow2_scale(__longlong_as_double((long long)rowmax[a])) : 1.0;
     scales[a] = s;
     unscale[a] = 1.0 / (sA[0] * s);
-}
-
-__device__ __forceinline__ void split2(double x, __half& hi, __half& lo)
-{
-    const float xf = (float)x;                         // |x| <= 2^14: conversion error 2^-24 relative, below the lo plane
-    hi = __float2half_rn(xf);
-    const double rem = x - (double)__half2float(hi);
-    lo = __float2half_rn((float)(rem * (double)LO_SCALE));
 }
 
 // F (k x len, column-major fp64) -> planes [NP][ld] (row a contiguous along i), rows >= k zero
@@ -480,62 +390,18 @@ k_split_matrix(const double* __restrict__ A, int64_t len, int64_t ncol, const do
 }
 
 // ---------------------------------------------------------------------------------------------------- host side
-using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeFn encode_fn()
-{
-    static EncodeFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        NNLM_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
-        if (!p || qres != cudaDriverEntryPointSuccess) throw Error(NNLM_E_CUDA, "cuTensorMapEncodeTiled is not available");
-        fn = reinterpret_cast<EncodeFn>(p);
-    }
-    return fn;
-}
-
-// 2-D fp16 tensor: inner extent `inner` (contiguous), `rows` rows of pitch ld elements; box = 64 x box_rows, SWIZZLE_128B
-CUtensorMap make_map(const __half* base, int64_t inner, int64_t rows, int64_t ld, int box_rows)
-{
-    CUtensorMap m;
-    const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(__half)};
-    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult rc = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
-                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS) throw Error(NNLM_E_CUDA, "cuTensorMapEncodeTiled failed (rc " + std::to_string((int)rc) + ")");
-    return m;
-}
-
-int sm_count()
-{
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
-
 template <int NP, int STAGES, int MODE>
 void launch_np(const CrossPlan& plan, const __half* a_hi, const __half* a_lo, const __half* f_hi, const __half* f_lo,
                const double* unscale, const double* center, const double* fsum, double* Qp, int drain, cudaStream_t st)
 {
-    constexpr size_t stage = MODE == 0 ? (2 * BM * BK * 2 + 2 * NP * BK * 2) : (BM * BK * 2 + NP * BK * 2);
+    constexpr size_t stage = MODE == 0 ? (2 * BM * BK * 2 + 2 * NP * BK * 2) : (MODE == 1 ? (BM * BK * 2 + NP * BK * 2) : (BM * BK * 2 + 2 * NP * BK * 2));
     constexpr size_t smem = (size_t)STAGES * stage + 1024 /*alignment slack*/ + 256;
     auto kern = k_cross_tc<NP, STAGES, MODE>;
     NNLM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const CUtensorMap mA_hi = make_map(a_hi, plan.len, plan.ncol, plan.ld_a, BM);
     const CUtensorMap mA_lo = MODE == 0 ? make_map(a_lo, plan.len, plan.ncol, plan.ld_a, BM) : mA_hi;
     const CUtensorMap mF_hi = make_map(f_hi, plan.len, NP, plan.ld_f, NP);
-    const CUtensorMap mF_lo = MODE == 0 ? make_map(f_lo, plan.len, NP, plan.ld_f, NP) : mF_hi;
+    const CUtensorMap mF_lo = MODE != 1 ? make_map(f_lo, plan.len, NP, plan.ld_f, NP) : mF_hi;
     CrossParams p;
     p.ncol = plan.ncol; p.kblocks = plan.kblocks; p.units = plan.units; p.k = plan.k; p.Qp = Qp; p.unscale = unscale;
     static const int drain_env = [] { const char* e = getenv("NNLM_TC_DRAIN"); return e ? atoi(e) : 0; }();
@@ -592,6 +458,15 @@ void launch_cross_tc_exact(const CrossPlan& plan, const __half* a_plane, const _
     launch_np<128, 6, 1>(plan, a_plane, nullptr, f_plane, nullptr, unscale, nullptr, nullptr, Qp, 64, st);
 }
 
+// Two consecutive slices in one pass (MODE 2): Qp = unscale[a] * sum_i (f0[a,i] + f1[a,i] / 2048) * a[i,j], exact: both partial
+// sums are integers below 2^24 and their fp64 combination spans 38 bits. unscale = the factor of slice f0.
+void launch_cross_tc_exact2(const CrossPlan& plan, const __half* a_plane, const __half* f0, const __half* f1, const double* unscale,
+                            double* Qp, cudaStream_t st)
+{
+    NNLM_REQUIRE(plan.np == 128, "the exact integer contraction runs on 128-row factor tiles");
+    launch_np<128, 4, 2>(plan, a_plane, nullptr, f0, f1, unscale, nullptr, nullptr, Qp, 64, st);
+}
+
 void launch_means(const double* A, int64_t len, int64_t ncol, double* colmean, double* rowmean, cudaStream_t st)
 {
     if (colmean) {
@@ -628,11 +503,82 @@ void launch_split_matrix(const double* A, int64_t len, int64_t ncol, const doubl
     NNLM_LAUNCHED();
 }
 
+// Row sums and row maxima of the factor in ONE pass, finished by the last CTA to arrive (fixed-order reduction of the
+// per-CTA partials, so the result does not depend on which CTA that is): fsum[a] = sum_i F[a,i] (the `sumW` of
+// src/update_with_missing.cpp:27 and the mean-correction term of the cross-product), scales / unscale as k_make_scales.
+// Replaces five launches of round 1 (memset, k_rowmax, k_make_scales, k_rowsum_partial, k_rowsum_finish).
+__global__ void __launch_bounds__(256)
+k_factor_prep(const double* __restrict__ F, int k, int64_t len, int64_t per_split, int np, const double* __restrict__ sA,
+              double* __restrict__ part /* [splits][2][k] */, unsigned int* __restrict__ ticket, double* __restrict__ fsum,
+              double* __restrict__ scales, double* __restrict__ unscale)
+{
+    __shared__ double sm[2][256];
+    __shared__ bool s_last;
+    const int groups = 256 / k;                                   // k <= 128
+    const int a = threadIdx.x % k, g = threadIdx.x / k;
+    const int64_t i_beg = (int64_t)blockIdx.x * per_split, i_end = min(len, i_beg + per_split);
+    double s = 0.0, mx = 0.0;
+    if (g < groups)
+        for (int64_t i = i_beg + g; i < i_end; i += groups) {
+            const double v = F[a + (int64_t)k * i];
+            s += v;
+            const double av = fabs(v);
+            if (!is_missing(av)) mx = fmax(mx, av);
+        }
+    sm[0][threadIdx.x] = s; sm[1][threadIdx.x] = mx;
+    __syncthreads();
+    if (threadIdx.x < k) {
+        double t = 0.0, m2 = 0.0;
+        for (int gg = 0; gg < groups; gg++) { t += sm[0][threadIdx.x + gg * k]; m2 = fmax(m2, sm[1][threadIdx.x + gg * k]); }
+        part[((int64_t)blockIdx.x * 2 + 0) * k + threadIdx.x] = t;
+        part[((int64_t)blockIdx.x * 2 + 1) * k + threadIdx.x] = m2;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int splits = gridDim.x;
+    for (int r = warp; r < np; r += 8) {                          // one warp per row, lanes stride the partials in a fixed order
+        double t = 0.0, m2 = 0.0;
+        if (r < k)
+            for (int sp = lane; sp < splits; sp += 32) {
+                t += part[((int64_t)sp * 2 + 0) * k + r];
+                m2 = fmax(m2, part[((int64_t)sp * 2 + 1) * k + r]);
+            }
+        t = warp_sum(t);
+#pragma unroll
+        for (int x = 16; x > 0; x >>= 1) m2 = fmax(m2, __shfl_xor_sync(0xffffffffu, m2, x));
+        if (lane == 0) {
+            const double sc = (r < k) ? pow2_scale(m2) : 1.0;
+            if (r < k) fsum[r] = t;
+            scales[r] = sc;
+            unscale[r] = 1.0 / (sA[0] * sc);
+        }
+    }
+    if (threadIdx.x == 0) *ticket = 0;                            // ready for the next half-iteration
+}
+
 void launch_rowmax(const double* F, int k, int64_t len, unsigned long long* rowmax, cudaStream_t st)
 {
     NNLM_CUDA_CHECK(cudaMemsetAsync(rowmax, 0, sizeof(unsigned long long) * k, st));
     const int64_t total = (int64_t)k * len;
     k_rowmax<<<(int)std::min<int64_t>(ceil_div(total, 256 * 8), 148 * 4), 256, sizeof(unsigned long long) * k, st>>>(F, k, len, rowmax);
+    NNLM_LAUNCHED();
+}
+
+void launch_factor_prep(const double* F, int k, int64_t len, int64_t ld, int np, const double* sA, double* part, int splits,
+                        unsigned int* ticket, double* fsum, double* scales, double* unscale, __half* hi, __half* lo, cudaStream_t st)
+{
+    NNLM_REQUIRE(k >= 1 && k <= 128, "factor preparation supports k <= 128");
+    const int64_t per_split = ceil_div(len, splits);
+    k_factor_prep<<<splits, 256, 0, st>>>(F, k, len, per_split, np, sA, part, ticket, fsum, scales, unscale);
+    NNLM_LAUNCHED();
+    const size_t smem = sizeof(double) * 64 * (k + 1);
+    if (smem > 48 * 1024) NNLM_CUDA_CHECK(cudaFuncSetAttribute(k_split_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_split_factor<<<(unsigned)ceil_div(ld, 64), 256, smem, st>>>(F, k, len, ld, np, scales, hi, lo);
     NNLM_LAUNCHED();
 }
 

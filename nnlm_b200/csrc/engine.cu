@@ -100,7 +100,7 @@ void Engine::ensure_scratch()
 {
     const int64_t big = std::max(n_, m_);
     gram_part_.alloc((size_t)gram_splits(big) * k_ * k_);
-    rowsum_part_.alloc((size_t)gram_splits(big) * k_);
+    rowsum_part_.alloc((size_t)gram_splits(big) * k_ * 2);
     G_.alloc((size_t)k_ * k_);
     Graw_.alloc((size_t)k_ * k_);
     G2_.alloc((size_t)k_ * k_);
@@ -126,7 +126,8 @@ void Engine::ensure_scratch()
     rp = std::max<size_t>(rp, (size_t)stats_part_count(big) * 3);
     red_part_.alloc(rp);
     small_.alloc(16);
-    tpc_scratch_.alloc(scd_tpc_scratch_doubles());
+    tpc_scratch_.alloc(scd_tpc_scratch_doubles());      // [0]: the solver's group counter, [1]: the ticket of k_factor_prep
+    NNLM_CUDA_CHECK(cudaMemsetAsync(tpc_scratch_.p, 0, tpc_scratch_.bytes(), st_));
     sweeps_.alloc(1);
     host_small_.alloc(16);
     NNLM_CUDA_CHECK(cudaMemsetAsync(sweeps_.p, 0, sizeof(unsigned long long), st_));
@@ -429,8 +430,8 @@ void Engine::run_half_tc(const Half& h)
     fork_gram(h, missing);
     if (h.ncol > 0) {
         timer.begin(KernelTimer::GRAM, st_);
-        launch_split_factor(h.Y, k_, h.len, plan.ld_f, plan.np, scale_a_.p, rowmax_.p, fscales_.p, unscale_.p, f_hi_.p, f_lo_.p, st_);
-        launch_rowsum(h.Y, k_, h.len, rowsum_part_.p, sumY_.p, st_);
+        launch_factor_prep(h.Y, k_, h.len, plan.ld_f, plan.np, scale_a_.p, rowsum_part_.p, gram_splits(h.len),
+                           reinterpret_cast<unsigned int*>(tpc_scratch_.p) + 1, sumY_.p, fscales_.p, unscale_.p, f_hi_.p, f_lo_.p, st_);
         timer.end(st_);
         timer.begin(KernelTimer::CROSS, st_);
         launch_cross_tc(plan, h.w_side ? t_hi_.p : a_hi_.p, h.w_side ? t_lo_.p : a_lo_.p, f_hi_.p, f_lo_.p, unscale_.p,
@@ -559,6 +560,8 @@ void Engine::errors(ErrorTerms* out, bool want_kl)
     timer.begin(KernelTimer::ERROR, st_);
     NNLM_CUDA_CHECK(cudaMemsetAsync(small_.p, 0, 2 * sizeof(double), st_));
     const bool identity = !want_kl && q_valid_;
+    // the fast square-loss storage evaluates both losses on the tensor cores (error_tc.cu); its KL sum includes the constant term
+    const bool tc_error = storage_ == Storage::F16X2 && error_tc_supported(k_) && std::getenv("NNLM_ERR_FP64") == nullptr;
     if (identity) {
         // sum (A - W'H)^2 = ||A||^2 - 2 <H, WtA> + <WtW, HHt>: WtA is what the H-half just contracted (its split-K slots are
         // still in Qp_), WtW its raw Gram; only the k x k Gram of the new H is formed here. All fp64, O(k m + k^2).
@@ -569,7 +572,14 @@ void Engine::errors(ErrorTerms* out, bool want_kl)
     } else if (mc_ > 0) {
         // this rank's columns of A against the whole W and its columns of H
         if (storage_ == Storage::F64) launch_error<double>(A64_.p, Wt_.p, H_.p + (size_t)k_ * c0_, k_, n_, mc_, red_part_.p, small_.p, st_);
-        else launch_error<float>(A32_.p, Wt_.p, H_.p + (size_t)k_ * c0_, k_, n_, mc_, red_part_.p, small_.p, st_);
+        else if (tc_error) {
+            const int kp = error_tc_kp(k_);
+            ew_hi_.ensure((size_t)n_ * kp); ew_lo_.ensure((size_t)n_ * kp); rsw_.ensure(n_);
+            eh_hi_.ensure((size_t)mc_ * kp); eh_lo_.ensure((size_t)mc_ * kp); rsh_.ensure(mc_);
+            launch_split_rows(Wt_.p, k_, n_, ew_hi_.p, ew_lo_.p, rsw_.p, st_);
+            launch_split_rows(H_.p + (size_t)k_ * c0_, k_, mc_, eh_hi_.p, eh_lo_.p, rsh_.p, st_);
+            launch_error_tc(A32_.p, n_, mc_, k_, ew_hi_.p, ew_lo_.p, rsw_.p, eh_hi_.p, eh_lo_.p, rsh_.p, red_part_.p, small_.p, st_);
+        } else launch_error<float>(A32_.p, Wt_.p, H_.p + (size_t)k_ * c0_, k_, n_, mc_, red_part_.p, small_.p, st_);
     }
     if (comm_ && !identity) comm_->allreduce_sum_f64(small_.p, 2, st_);
     launch_factor_stats(Wt_.p, k_, n_, red_part_.p, small_.p + 2, st_);
@@ -583,7 +593,7 @@ void Engine::errors(ErrorTerms* out, bool want_kl)
         out->sum_kl = std::nan("");
     } else {
         out->sum_sq = host_small_.p[0];
-        out->sum_kl = host_small_.p[1];
+        out->sum_kl = host_small_.p[1] - (tc_error ? kl_const_sum_ : 0.0);
     }
     last_identity_ = identity;
     for (int i = 0; i < 3; i++) { out->w_stats[i] = host_small_.p[2 + i]; out->h_stats[i] = host_small_.p[5 + i]; }

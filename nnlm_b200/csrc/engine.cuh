@@ -161,6 +161,9 @@ private:
     DevBuf<__half> mk_, mkt_, zplanes_;
     DevBuf<double> zunscale_, Qp2_, S_;
     CrossPlan plan_na_h_, plan_na_w_;
+    // tensor-core error evaluation (error_tc.cu): row planes of W and of this rank's columns of H, their inverse scales
+    DevBuf<__half> ew_hi_, ew_lo_, eh_hi_, eh_lo_;
+    DevBuf<float> rsw_, rsh_;
     DevBuf<double> scale_a_, fscales_, unscale_, colmean_, rowmean_;
     DevBuf<unsigned long long> rowmax_;
     CrossPlan plan_h_, plan_w_;

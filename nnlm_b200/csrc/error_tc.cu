@@ -1,0 +1,278 @@
+// error_tc.cu — a8 on the tensor cores: the loss bookkeeping of the outer loop (src/nnmf.cpp:121-141, 164-177) for the
+// fast-precision path. The reference materialises Ahat = W.t()*H and makes two more passes over it (one with a log) at
+// every `trace` iteration — every SECOND iteration with R's default trace = 100 / inner.max.iter = 2 (R/nnmf.R:138). The
+// fp64 kernel of error_eval.cu never materialises Ahat but spends 2 n m k fp64 FMAs + n m fp64 logs (4.8 ms at config 2,
+// more than two whole ANLS iterations). Here a 128 x 128 tile of Ahat is ONE tcgen05 contraction over the rank
+// (K = 64 or 128) in TMEM and the epilogue folds it against the matching tile of A straight out of TMEM:
+//   * operands: W and H as fp16 hi/lo planes [row][K] (K-major: column i of the k x n factor is already contiguous), each
+//     row scaled by its own power of two, Ahat = (hi.hi + 2^-11 (hi.lo + lo.hi)) / (s_i t_j) — the scheme of cross_tc.cu;
+//   * square loss: r = a - Ahat in fp32 (Ahat carries ~2^-22 relative error, random in sign: 1e-6 of a residual of 0.1);
+//   * KL: the reference adds a constant term and a variable term that cancel to ~1e-5 of their size. Written per entry,
+//       [(a+e) log(a+e) - a] + [-(a+e) log(Ahat+e) + Ahat] = (a+e) * g(x),  x = (Ahat - a) / (a+e),  g(x) = x - log1p(x) >= 0,
+//     a sum of non-negative terms with no cancellation, which fp32 evaluates to ~1e-7 relative (series for |x| < 1/8);
+//     the kernel returns sum (a+e) g(x); the engine subtracts the constant term so callers keep adding it like the reference;
+//   * per-thread partial sums in fp32 over 64 entries, then fp64; CTA partials reduced in a fixed order.
+// HBM-bound on the one pass over the fp32 copy of A (2 GB at config 2). Missing entries (non-finite a) are skipped as
+// in src/nnmf.cpp:124-125. Warp roles as cross_tc.cu: warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue.
+#include <algorithm>
+
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace nnlm {
+
+using namespace tc;
+
+namespace {
+
+constexpr int TM = 128;            // rows of W (entries i) per tile
+constexpr int TN = 128;            // rows of H (columns j) per tile
+constexpr int TK = 64;             // rank elements per k-block (128 bytes of fp16)
+constexpr int E_EPI_WARPS = 8;
+constexpr int E_THREADS = 32 * (2 + E_EPI_WARPS);
+constexpr int E_STAGES = 3;
+constexpr int PLANE_BYTES = TM * TK * 2;                 // 16 KB (TM == TN)
+constexpr int STAGE_BYTES = 4 * PLANE_BYTES;             // W hi, W lo, H hi, H lo
+
+struct ErrParams {
+    int64_t n, m;              // rows of A, columns of A held by this rank
+    int64_t tiles_i, tiles_j;
+    int kblocks;               // ceil(k / 64)
+    const float* A;            // n x m column-major, non-finite = missing
+    const float* rsw;          // [n]  1 / s_i
+    const float* rsh;          // [m]  1 / t_j
+    double* part;              // [gridDim.x][2]
+};
+
+// g(x) = x - log1p(x), x > -1
+__device__ __forceinline__ float g_of(float x)
+{
+    if (fabsf(x) < 0.125f) {
+        // x^2 (1/2 - x/3 + x^2/4 - ... ): nine terms leave < 2e-9 relative
+        float p = 1.0f / 10.0f;
+        p = fmaf(-p, x, 1.0f / 9.0f);
+        p = fmaf(-p, x, 1.0f / 8.0f);
+        p = fmaf(-p, x, 1.0f / 7.0f);
+        p = fmaf(-p, x, 1.0f / 6.0f);
+        p = fmaf(-p, x, 1.0f / 5.0f);
+        p = fmaf(-p, x, 1.0f / 4.0f);
+        p = fmaf(-p, x, 1.0f / 3.0f);
+        p = fmaf(-p, x, 1.0f / 2.0f);
+        return x * x * p;
+    }
+    return x - log1pf(x);
+}
+
+__global__ void __launch_bounds__(E_THREADS, 1)
+k_error_tc(const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo,
+           const __grid_constant__ CUtensorMap mapH_hi, const __grid_constant__ CUtensorMap mapH_lo, const ErrParams p)
+{
+    constexpr uint32_t TMEM_COLS = 512;                  // 2 buffers x (d0 | d1) x 128 columns
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);   // f16 x f16 -> f32, K-major
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* tiles = smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + E_STAGES * STAGE_BYTES);
+    uint64_t* empty = full + E_STAGES;
+    uint64_t* tfull = empty + E_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    double* red = reinterpret_cast<double*>(tmem_slot + 2);          // [E_EPI_WARPS][2]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ntiles = p.tiles_i * p.tiles_j;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < E_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], E_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================== TMA producer: one stage per (tile, k-block) =====================================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int r0 = (int)((t % p.tiles_i) * TM), c0 = (int)((t / p.tiles_i) * TN);
+                for (int kb = 0; kb < p.kblocks; kb++) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* sa = tiles + stage * STAGE_BYTES;
+                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    tma_load_2d(sa, &mapW_hi, &full[stage], kb * TK, r0);
+                    tma_load_2d(sa + PLANE_BYTES, &mapW_lo, &full[stage], kb * TK, r0);
+                    tma_load_2d(sa + 2 * PLANE_BYTES, &mapH_hi, &full[stage], kb * TK, c0);
+                    tma_load_2d(sa + 3 * PLANE_BYTES, &mapH_lo, &full[stage], kb * TK, c0);
+                    if (++stage == E_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =====================================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            uint32_t it = 0;
+            for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
+                const uint32_t buf = it & 1, tph = (it >> 1) & 1;
+                mbar_wait(&tempty[buf], tph ^ 1);
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + buf * (2 * TN), d1 = d0 + TN;
+                for (int kb = 0; kb < p.kblocks; kb++) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(tiles + stage * STAGE_BYTES);
+                    const uint64_t w_hi = make_desc(sa), w_lo = make_desc(sa + PLANE_BYTES);
+                    const uint64_t h_hi = make_desc(sa + 2 * PLANE_BYTES), h_lo = make_desc(sa + 3 * PLANE_BYTES);
+#pragma unroll
+                    for (int ks = 0; ks < TK / 16; ks++) {
+                        const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+                        const uint32_t acc = (kb == 0 && ks == 0) ? 0u : 1u;
+                        umma_f16(d0, w_hi + adv, h_hi + adv, IDESC, acc);
+                        umma_f16(d1, w_hi + adv, h_lo + adv, IDESC, acc);
+                        umma_f16(d1, w_lo + adv, h_hi + adv, IDESC, 1u);
+                    }
+                    tc_commit(&empty[stage]);
+                    if (++stage == E_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull[buf]);
+            }
+        }
+    } else {
+        // ===================================== epilogue: TMEM tile of Ahat against the tile of A =====================================
+        const int ew = warp - 2;
+        const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
+        const int half = ew >> 2;                      // which 64 columns of the tile
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        double acc_sq = 0.0, acc_kl = 0.0;
+        uint32_t it = 0;
+        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
+            const int64_t i = (t % p.tiles_i) * TM + quarter * 32 + lane;
+            const int64_t j0 = (t / p.tiles_i) * TN + half * 64;
+            const uint32_t buf = it & 1, tph = (it >> 1) & 1;
+            const bool row_ok = i < p.n;
+            const float ri = row_ok ? p.rsw[i] : 0.0f;
+            mbar_wait(&tfull[buf], tph);
+            tc_fence_after();
+            float sq = 0.0f, kl = 0.0f;
+#pragma unroll
+            for (int ch = 0; ch < 2; ch++) {
+                uint32_t r0[32], r1[32];
+                const uint32_t t0 = tmem_base + lane_addr + buf * (2 * TN) + half * 64 + ch * 32;
+                TmemLd<32>::ld(t0, r0);
+                TmemLd<32>::ld(t0 + TN, r1);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (ch == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[buf]);          // the MMA of the tile after next may overwrite this buffer
+                }
+#pragma unroll
+                for (int c = 0; c < 32; c++) {
+                    const int64_t j = j0 + ch * 32 + c;
+                    if (row_ok && j < p.m) {
+                        const float a = p.A[i + p.n * j];
+                        if (((__float_as_uint(a) >> 23) & 0xffu) != 0xffu) {                  // finite: src/nnmf.cpp:124-125
+                            const float ah = fmaf(__uint_as_float(r1[c]), (float)LO_UNSCALE, __uint_as_float(r0[c])) * (ri * p.rsh[j]);
+                            const float r = a - ah;
+                            sq = fmaf(r, r, sq);
+                            const float ae = a + 1e-16f;
+                            const float x = __fdividef(ah - a, ae);
+                            // Ahat ~ 0 against a > 0 (x -> -1, beyond fp32's resolution of 1 + x): the same quantity written as
+                            // (a+e) log((a+e) / (Ahat+e)) + Ahat - a, which has no cancellation there
+                            kl += (x < -0.9999f) ? fmaf(ae, __logf(ae) - __logf(ah + 1e-16f), ah - a) : ae * g_of(x);
+                        }
+                    }
+                }
+            }
+            acc_sq += (double)sq;
+            acc_kl += (double)kl;
+        }
+        acc_sq = warp_sum(acc_sq);
+        acc_kl = warp_sum(acc_kl);
+        if (lane == 0) { red[2 * ew] = acc_sq; red[2 * ew + 1] = acc_kl; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int w = 0; w < E_EPI_WARPS; w++) { a0 += red[2 * w]; a1 += red[2 * w + 1]; }
+        p.part[2 * blockIdx.x] = a0;
+        p.part[2 * blockIdx.x + 1] = a1;
+    }
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// X (k x cols, column-major fp64) -> planes [cols][KP] (row i = column i of X, zero beyond k), rs[i] = 1 / (power-of-two scale)
+__global__ void __launch_bounds__(256)
+k_split_rows(const double* __restrict__ X, int k, int64_t cols, int kp, __half* __restrict__ hi, __half* __restrict__ lo,
+             float* __restrict__ rs)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;           // one warp per row
+    if (row >= cols) return;
+    double mx = 0.0;
+    for (int c = lane; c < k; c += 32) {
+        const double v = fabs(X[c + (int64_t)k * row]);
+        if (!is_missing(v)) mx = fmax(mx, v);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+    const double sc = pow2_scale(mx);
+    if (lane == 0) rs[row] = (float)(1.0 / sc);
+    for (int c = lane; c < kp; c += 32) {
+        __half h = __float2half_rn(0.f), l = h;
+        if (c < k) split2(X[c + (int64_t)k * row] * sc, h, l);
+        hi[row * kp + c] = h;
+        lo[row * kp + c] = l;
+    }
+}
+
+}  // namespace
+
+bool error_tc_supported(int k) { return k >= 1 && k <= 128; }
+int error_tc_kp(int k) { return k <= 64 ? 64 : 128; }
+int error_tc_grid(int64_t n, int64_t m) { return (int)std::min<int64_t>(sm_count(), ceil_div(n, TM) * ceil_div(m, TN)); }
+
+void launch_split_rows(const double* X, int k, int64_t cols, __half* hi, __half* lo, float* rs, cudaStream_t st)
+{
+    if (cols <= 0) return;
+    k_split_rows<<<(unsigned)ceil_div(cols * 32, 256), 256, 0, st>>>(X, k, cols, error_tc_kp(k), hi, lo, rs);
+    NNLM_LAUNCHED();
+}
+
+// out[0] = sum over finite a of (a - Ahat)^2; out[1] = sum over finite a of (a+e) g(x) = the reference's constant KL term
+// sum[(a+e) log(a+e) - a] (src/nnmf.cpp:70-73) PLUS its variable term sum[-(a+e) log(Ahat+e) + Ahat] (:125,139): the caller
+// subtracts the constant it already holds. A: n x m fp32 column-major; W planes [n][kp], H planes [m][kp] (launch_split_rows);
+// part: 2 * error_tc_grid doubles.
+void launch_error_tc(const float* A, int64_t n, int64_t m, int k, const __half* w_hi, const __half* w_lo, const float* rsw,
+                     const __half* h_hi, const __half* h_lo, const float* rsh, double* part, double* out, cudaStream_t st)
+{
+    NNLM_REQUIRE(error_tc_supported(k), "tensor-core error evaluation supports rank k <= 128");
+    const int kp = error_tc_kp(k);
+    constexpr size_t smem = (size_t)E_STAGES * STAGE_BYTES + 1024 + 512;
+    NNLM_CUDA_CHECK(cudaFuncSetAttribute(k_error_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ErrParams p;
+    p.n = n; p.m = m; p.tiles_i = ceil_div(n, TM); p.tiles_j = ceil_div(m, TN); p.kblocks = kp / TK;
+    p.A = A; p.rsw = rsw; p.rsh = rsh; p.part = part;
+    const CUtensorMap mW_hi = make_map(w_hi, kp, n, kp, TM), mW_lo = make_map(w_lo, kp, n, kp, TM);
+    const CUtensorMap mH_hi = make_map(h_hi, kp, m, kp, TN), mH_lo = make_map(h_lo, kp, m, kp, TN);
+    const int grid = error_tc_grid(n, m);
+    k_error_tc<<<grid, E_THREADS, smem, st>>>(mW_hi, mW_lo, mH_hi, mH_lo, p);
+    NNLM_LAUNCHED();
+    launch_reduce_partials(part, grid, 2, out, st);
+}
+
+}  // namespace nnlm

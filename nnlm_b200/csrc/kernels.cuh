@@ -89,11 +89,17 @@ void launch_split_matrix(const double* A, int64_t len, int64_t ncol, const doubl
 // F (k x len col-major fp64) -> planes [np][ld] with per-row power-of-two scales; unscale[a] = 1/(sA*scale[a])
 void launch_split_factor(const double* F, int k, int64_t len, int64_t ld, int np, const double* sA, unsigned long long* rowmax,
                          double* scales, double* unscale, __half* hi, __half* lo, cudaStream_t st);
+// The same plus fsum = rowSums(F) in two launches: one pass for row sums and maxima (finished by the last CTA), one for the
+// planes. part: 2 * splits * k doubles (splits = gram_splits(len)); ticket: one zero-initialised counter owned by the caller.
+void launch_factor_prep(const double* F, int k, int64_t len, int64_t ld, int np, const double* sA, double* part, int splits,
+                        unsigned int* ticket, double* fsum, double* scales, double* unscale, __half* hi, __half* lo, cudaStream_t st);
 // rowmax[a] = bit pattern of max_i |F[a,i]| (zeroed here)
 void launch_rowmax(const double* F, int k, int64_t len, unsigned long long* rowmax, cudaStream_t st);
 // exact contraction of integer-valued fp16 planes (cross_tc.cu MODE 1); plan from cross_tc_plan(128, len, ncol)
 void launch_cross_tc_exact(const CrossPlan& plan, const __half* a_plane, const __half* f_plane, const double* unscale, double* Qp,
                            cudaStream_t st);
+void launch_cross_tc_exact2(const CrossPlan& plan, const __half* a_plane, const __half* f0, const __half* f1, const double* unscale,
+                            double* Qp, cudaStream_t st);
 
 // ---- solve_ls.cu: K3/K4/K5 — warp-per-column sequential coordinate descent / Lee multiplicative, square loss ----
 // X (k x ncol) in/out; G regularised Gram (k x k); Qp split-K partials of Wt*A (splits x k x ncol); mask k x ncol bytes or null;
@@ -166,6 +172,16 @@ void launch_dot_factor_cross(const double* X, const double* Qp, int splits, int 
 void launch_dot_small(const double* a, const double* b, int count, double* out, cudaStream_t st);   // out[0] = <a, b>
 // out[0] = sum X^2, out[1] = sum X, out[2] = sum_i (sum_a X[a,i])^2 = accu(X*X.t())   (src/nnmf.cpp:224-240)
 int64_t stats_part_count(int64_t cols);
+
+// ---- error_tc.cu: a8 on the tensor cores (fast-precision path) ----
+bool error_tc_supported(int k);
+int  error_tc_kp(int k);                       // padded rank of the row planes: 64 or 128
+int  error_tc_grid(int64_t n, int64_t m);      // CTAs = partial records
+// X (k x cols, column-major) -> fp16 planes [cols][kp] with one power-of-two scale per row; rs[i] = 1 / scale
+void launch_split_rows(const double* X, int k, int64_t cols, __half* hi, __half* lo, float* rs, cudaStream_t st);
+// out[0] = sum (A - W'H)^2, out[1] = sum (A+e) g((W'H - A) / (A+e)) over the finite entries (see the file header)
+void launch_error_tc(const float* A, int64_t n, int64_t m, int k, const __half* w_hi, const __half* w_lo, const float* rsw,
+                     const __half* h_hi, const __half* h_lo, const float* rsh, double* part, double* out, cudaStream_t st);
 void launch_factor_stats(const double* X, int k, int64_t cols, double* part, double* out, cudaStream_t st);
 
 }  // namespace nnlm

@@ -15,8 +15,8 @@
 // accumulator holds the exact sum of up to 2^13 of them; the cross-product kernel drains it into fp64 every 4096 indices
 // (cross_tc.cu MODE 1). The only error is the 2^-44 truncation of Z relative to the column bound: measured against the
 // fp64 per-column Gram in tests/test_gpu_na_path.py.
-// Cost per half-iteration at config 4: ceil(1325 / 128) = 11 tiles of 128 Z-columns x 4 slices = 44 launches of the
-// HBM-bound cross-product kernel over the fp16 mask plane.
+// Cost per half-iteration at config 4: ceil(1325 / 128) = 11 tiles of 128 Z-columns x 2 slice pairs = 22 passes of the
+// HBM-bound cross-product kernel over the fp16 mask plane (two slices share one pass: cross_tc.cu MODE 2).
 #include <algorithm>
 
 #include "kernels.cuh"
@@ -26,6 +26,7 @@ namespace nnlm {
 namespace {
 
 constexpr int ZS = NA_SLICES;      // slices per Z column
+static_assert(NA_SLICES % 2 == 0, "slices go through the contraction in pairs");
 constexpr int ZT = NA_TILE;        // Z columns (factor-plane rows) per contraction
 
 __device__ __forceinline__ int pair_a_of(int p)      // p = a (a + 1) / 2 + b, b <= a
@@ -167,8 +168,9 @@ void launch_na_gram_tc(const CrossPlan& plan, const double* Y, int k, const __ha
     for (int p0 = 0; p0 < npairs; p0 += ZT) {
         k_z_slices<<<(unsigned)ceil_div(ld, 64), 256, smem, st>>>(Y, k, len, ld, rowmax, p0, npairs, zplanes, zunscale);
         NNLM_LAUNCHED();
-        for (int s = 0; s < ZS; s++) {
-            launch_cross_tc_exact(plan, mask_plane, zplanes + (size_t)s * ZT * ld, zunscale + s * ZT, Qp, st);
+        for (int s = 0; s < ZS; s += 2) {              // two slices per pass over the mask plane
+            launch_cross_tc_exact2(plan, mask_plane, zplanes + (size_t)s * ZT * ld, zplanes + (size_t)(s + 1) * ZT * ld,
+                                   zunscale + s * ZT, Qp, st);
             k_fold<<<(int)std::min<int64_t>(ceil_div(ncol * ZT, 256), 148 * 16), 256, 0, st>>>(Qp, plan.slots, ncol, pt, p0, S);
             NNLM_LAUNCHED();
         }

@@ -22,9 +22,13 @@ namespace nnlm {
 // gs: shared Gram, gs[r + KR*c] = V[r,c], rows >= k zero. Returns the number of sweeps performed.
 template <int RPL, int METHOD>
 __device__ __forceinline__ unsigned warp_solve_ls(double (&h)[RPL], const double (&q)[RPL], const unsigned (&mk)[RPL],
-                                                  const double* gs, int k, double l1, unsigned max_iter, double rel_tol)
+                                                  const double* gs, int k, double l1, unsigned max_iter, double rel_tol,
+                                                  int ldg = 32 * RPL)
 {
-    constexpr int KR = 32 * RPL;
+    // ldg: column pitch of the shared Gram. The dense solver pads every column to 32*RPL rows of zeros; the NA solver packs
+    // the columns at pitch k (more columns in flight per SM): lanes whose row is >= k then read finite values of the next
+    // column into a mu that is never consumed (their h is 0, their 1/V_rr is 0 and they never own a coordinate).
+    const int KR = ldg;
     const int lane = threadIdx.x & 31;
     unsigned t = 0;
     bool cont = true;                                   // rel_err starts at 1 + rel_tol

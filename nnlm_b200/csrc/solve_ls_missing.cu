@@ -227,19 +227,19 @@ k_solve_batch(double* __restrict__ X, const double* __restrict__ Gin, const doub
 // Kernel B': as kernel B, with the per-column Gram assembled on the fly from the shared raw Gram and the packed tensor-core
 // corrections of na_gram.cu: G_j[a,b] = Gfull[a,b] - S[j][pair(max, min)] + regularisation (src/update_with_missing.cpp:98-103).
 template <int RPL, int METHOD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_solve_batch_packed(double* __restrict__ X, const double* __restrict__ Gfull, const double* __restrict__ S, int64_t pt,
                      const double* __restrict__ Qp, int splits, const double* __restrict__ center, const uint8_t* __restrict__ mask,
                      int k, int64_t ncol, double p0, double p1, double l1, unsigned max_iter, double rel_tol,
                      unsigned long long* __restrict__ sweeps)
 {
-    constexpr int KR = 32 * RPL;
     extern __shared__ __align__(32) double smd[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-    double* gs = smd + (size_t)warp * KR * KR;      // [KR][KR] column-major, rows / columns >= k zero
+    const int per_warp = k * k + 32 * RPL;           // columns packed at pitch k + slack for the lanes beyond row k (solve_core.cuh)
+    double* gs = smd + (size_t)warp * per_warp;
     unsigned long long my_sweeps = 0;
     const int kk2 = k * (k + 1) / 2;
-    for (int e = lane; e < KR * KR; e += 32) gs[e] = 0.0;
+    for (int e = lane; e < per_warp; e += 32) gs[e] = 0.0;
     for (int64_t col = (int64_t)blockIdx.x * wpc + warp; col < ncol; col += (int64_t)gridDim.x * wpc) {
         const uint8_t* mcol = mask ? mask + (int64_t)k * col : nullptr;
         if (mcol) {                                          // src/update_with_missing.cpp:77-78
@@ -249,14 +249,18 @@ k_solve_batch_packed(double* __restrict__ X, const double* __restrict__ Gfull, c
         }
         __syncwarp();
         const double* Sj = S + pt * col;
-        for (int e = lane; e < k * k; e += 32) {
-            const int a = e % k, b = e / k;
-            const int hi = a > b ? a : b, lo = a > b ? b : a;
-            double g = Gfull[e] - Sj[hi * (hi + 1) / 2 + lo];
+        // lower triangle from the packed corrections (contiguous reads), mirrored: G_j = Gfull - S_j + regularisation (:98-103)
+        for (int p = lane; p < kk2; p += 32) {
+            int a = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+            while ((a + 1) * (a + 2) / 2 <= p) a++;
+            while (a * (a + 1) / 2 > p) a--;
+            const int b = p - a * (a + 1) / 2;
+            double g = Gfull[a + k * b] - Sj[p];
             if (p0 != p1 && a == b) g += p0 - p1;
             if (p1 != 0.0) g += p1;
             if (a == b) g += TINY_NUM;
-            gs[a + KR * b] = g;
+            gs[a + k * b] = g;
+            gs[b + k * a] = g;
         }
         __syncwarp();
         double h[RPL], q[RPL];
@@ -276,7 +280,7 @@ k_solve_batch_packed(double* __restrict__ X, const double* __restrict__ Gfull, c
             const bool mb = valid && mcol != nullptr && mcol[r] != 0;
             mk[s] = __ballot_sync(0xffffffffu, mb);
         }
-        my_sweeps += warp_solve_ls<RPL, METHOD>(h, q, mk, gs, k, l1, max_iter, rel_tol);
+        my_sweeps += warp_solve_ls<RPL, METHOD>(h, q, mk, gs, k, l1, max_iter, rel_tol, k);
 #pragma unroll
         for (int s = 0; s < RPL; s++) {
             const int r = lane + 32 * s;
@@ -291,12 +295,12 @@ void launch_packed_rpl(int method, double* X, const double* Gfull, const double*
                        const double* center, const uint8_t* mask, int k, int64_t ncol, const double* pen, unsigned max_iter,
                        double rel_tol, unsigned long long* sweeps, cudaStream_t st)
 {
-    constexpr int KR = 32 * RPL;
-    const int wpc = std::max(1, std::min(7, (int)(220 * 1024 / (sizeof(double) * KR * KR))));
-    const size_t smem = sizeof(double) * (size_t)wpc * KR * KR;
+    const size_t per_warp = sizeof(double) * ((size_t)k * k + 32 * RPL);
+    const int wpc = std::max(1, std::min(16, (int)(220 * 1024 / per_warp)));      // columns in flight per SM
+    const size_t smem = (size_t)wpc * per_warp;
     auto kb = method == 1 ? k_solve_batch_packed<RPL, 1> : k_solve_batch_packed<RPL, 2>;
     NNLM_CUDA_CHECK(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(ncol, wpc), 148 * 4));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(ncol, wpc), 148));
     kb<<<grid, 32 * wpc, smem, st>>>(X, Gfull, S, pt, Qp, splits, center, mask, k, ncol, pen[0], pen[1], pen[2], max_iter, rel_tol, sweeps);
     NNLM_LAUNCHED();
 }
