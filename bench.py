@@ -352,13 +352,13 @@ def main():
             tpeak, tsrc = float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json bf16_tflops burst; fp16 runs at the same rate)"
         except Exception:
             pass
-        launches_per_half = -(-P // 128) * 4
+        launches_per_half = -(-P // 128) * 2          # 128 Z columns x 2 slices per pass over the mask plane
         mask_bytes = 2.0 * launches_per_half * n * m * 2 / world
         roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None,
-                    "kernel": "k_cross_tc<128,6,1> x %d launches per half (mask x Khatri-Rao slices) + k_z_slices + k_fold, per GPU" % launches_per_half,
+                    "kernel": "k_cross_tc<128,4,2> x %d launches per half (mask x Khatri-Rao slices, two slices per pass) + k_z_slices + k_fold, per GPU" % launches_per_half,
                     "algorithmic_flop_per_step": flops, "ms_per_step_in_these_kernels": t * 1e3, "peak_source": tsrc,
                     "hbm_side": {"achieved": mask_bytes / t / 1e9 if t > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
-                                 "bytes_per_step": mask_bytes, "what": "fp16 mask plane streamed once per launch"},
+                                 "bytes_per_step": mask_bytes, "what": "fp16 mask plane streamed once per launch (the two slice planes of Z come from L2: 2x these bytes)"},
                     "solve_ms_per_step": st["solve_ms"] / args.steps}
     roofline["share_of_step"] = share
     if cross:

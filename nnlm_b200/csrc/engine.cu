@@ -574,10 +574,11 @@ void Engine::errors(ErrorTerms* out, bool want_kl)
         if (storage_ == Storage::F64) launch_error<double>(A64_.p, Wt_.p, H_.p + (size_t)k_ * c0_, k_, n_, mc_, red_part_.p, small_.p, st_);
         else if (tc_error) {
             const int kp = error_tc_kp(k_);
-            ew_hi_.ensure((size_t)n_ * kp); ew_lo_.ensure((size_t)n_ * kp); rsw_.ensure(n_);
-            eh_hi_.ensure((size_t)mc_ * kp); eh_lo_.ensure((size_t)mc_ * kp); rsh_.ensure(mc_);
-            launch_split_rows(Wt_.p, k_, n_, ew_hi_.p, ew_lo_.p, rsw_.p, st_);
-            launch_split_rows(H_.p + (size_t)k_ * c0_, k_, mc_, eh_hi_.p, eh_lo_.p, rsh_.p, st_);
+            ew_hi_.ensure((size_t)n_ * kp); ew_lo_.ensure((size_t)n_ * kp); rsw_.ensure(4);
+            eh_hi_.ensure((size_t)mc_ * kp); eh_lo_.ensure((size_t)mc_ * kp); rsh_.ensure(4);
+            unsigned long long* mxb = reinterpret_cast<unsigned long long*>(small_.p + 10);
+            launch_split_rows(Wt_.p, k_, n_, ew_hi_.p, ew_lo_.p, rsw_.p, mxb, st_);
+            launch_split_rows(H_.p + (size_t)k_ * c0_, k_, mc_, eh_hi_.p, eh_lo_.p, rsh_.p, mxb + 1, st_);
             launch_error_tc(A32_.p, n_, mc_, k_, ew_hi_.p, ew_lo_.p, rsw_.p, eh_hi_.p, eh_lo_.p, rsh_.p, red_part_.p, small_.p, st_);
         } else launch_error<float>(A32_.p, Wt_.p, H_.p + (size_t)k_ * c0_, k_, n_, mc_, red_part_.p, small_.p, st_);
     }

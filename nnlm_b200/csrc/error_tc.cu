@@ -5,15 +5,15 @@
 // more than two whole ANLS iterations). Here a 128 x 128 tile of Ahat is ONE tcgen05 contraction over the rank
 // (K = 64 or 128) in TMEM and the epilogue folds it against the matching tile of A straight out of TMEM:
 //   * operands: W and H as fp16 hi/lo planes [row][K] (K-major: column i of the k x n factor is already contiguous), each
-//     row scaled by its own power of two, Ahat = (hi.hi + 2^-11 (hi.lo + lo.hi)) / (s_i t_j) — the scheme of cross_tc.cu;
+//     factor scaled by one power of two, Ahat = (hi.hi + 2^-11 (hi.lo + lo.hi)) / (s_W s_H) — the scheme of cross_tc.cu;
 //   * square loss: r = a - Ahat in fp32 (Ahat carries ~2^-22 relative error, random in sign: 1e-6 of a residual of 0.1);
 //   * KL: the reference adds a constant term and a variable term that cancel to ~1e-5 of their size. Written per entry,
 //       [(a+e) log(a+e) - a] + [-(a+e) log(Ahat+e) + Ahat] = (a+e) * g(x),  x = (Ahat - a) / (a+e),  g(x) = x - log1p(x) >= 0,
 //     a sum of non-negative terms with no cancellation, which fp32 evaluates to ~1e-7 relative (series for |x| < 1/8);
 //     the kernel returns sum (a+e) g(x); the engine subtracts the constant term so callers keep adding it like the reference;
-//   * per-thread partial sums in fp32 over 64 entries, then fp64; CTA partials reduced in a fixed order.
+//   * per-thread partial sums in fp32 over 32 entries, then fp64; CTA partials reduced in a fixed order.
 // HBM-bound on the one pass over the fp32 copy of A (2 GB at config 2). Missing entries (non-finite a) are skipped as
-// in src/nnmf.cpp:124-125. Warp roles as cross_tc.cu: warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue.
+// in src/nnmf.cpp:124-125. Warp roles as cross_tc.cu: warp 0 TMA producer, warp 1 MMA issuer, warps 2..17 epilogue.
 #include <algorithm>
 
 #include "kernels.cuh"
@@ -28,7 +28,7 @@ namespace {
 constexpr int TM = 128;            // rows of W (entries i) per tile
 constexpr int TN = 128;            // rows of H (columns j) per tile
 constexpr int TK = 64;             // rank elements per k-block (128 bytes of fp16)
-constexpr int E_EPI_WARPS = 8;
+constexpr int E_EPI_WARPS = 16;         // four per TMEM lane quarter, 32 columns of the tile each
 constexpr int E_THREADS = 32 * (2 + E_EPI_WARPS);
 constexpr int E_STAGES = 3;
 constexpr int PLANE_BYTES = TM * TK * 2;                 // 16 KB (TM == TN)
@@ -39,28 +39,34 @@ struct ErrParams {
     int64_t tiles_i, tiles_j;
     int kblocks;               // ceil(k / 64)
     const float* A;            // n x m column-major, non-finite = missing
-    const float* rsw;          // [n]  1 / s_i
-    const float* rsh;          // [m]  1 / t_j
+    const float* rsw;          // [1]  1 / s_W (one power-of-two scale per factor: the fp16 halves are floating-point, so
+    const float* rsh;          // [1]  1 / s_H  every entry keeps its 22 bits down to 2^-27 of the largest one)
     double* part;              // [gridDim.x][2]
 };
 
-// g(x) = x - log1p(x), x > -1
-__device__ __forceinline__ float g_of(float x)
+// g(x) = x - log1p(x) for |x| < 1/8 as x^2 (1/2 - x/3 + x^2/4 - ...): nine terms leave < 2e-9 relative
+__device__ __forceinline__ float g_series(float x)
 {
-    if (fabsf(x) < 0.125f) {
-        // x^2 (1/2 - x/3 + x^2/4 - ... ): nine terms leave < 2e-9 relative
-        float p = 1.0f / 10.0f;
-        p = fmaf(-p, x, 1.0f / 9.0f);
-        p = fmaf(-p, x, 1.0f / 8.0f);
-        p = fmaf(-p, x, 1.0f / 7.0f);
-        p = fmaf(-p, x, 1.0f / 6.0f);
-        p = fmaf(-p, x, 1.0f / 5.0f);
-        p = fmaf(-p, x, 1.0f / 4.0f);
-        p = fmaf(-p, x, 1.0f / 3.0f);
-        p = fmaf(-p, x, 1.0f / 2.0f);
-        return x * x * p;
-    }
-    return x - log1pf(x);
+    float p = 1.0f / 10.0f;
+    p = fmaf(-p, x, 1.0f / 9.0f);
+    p = fmaf(-p, x, 1.0f / 8.0f);
+    p = fmaf(-p, x, 1.0f / 7.0f);
+    p = fmaf(-p, x, 1.0f / 6.0f);
+    p = fmaf(-p, x, 1.0f / 5.0f);
+    p = fmaf(-p, x, 1.0f / 4.0f);
+    p = fmaf(-p, x, 1.0f / 3.0f);
+    p = fmaf(-p, x, 1.0f / 2.0f);
+    return x * x * p;
+}
+
+// (a+e) g(x) for any x > -1. Ahat ~ 0 against a > 0 (x -> -1, beyond fp32's resolution of 1 + x) is written as
+// (a+e) log((a+e) / (Ahat+e)) + Ahat - a, which has no cancellation there.
+__device__ __noinline__ float kl_term_general(float a, float ah)
+{
+    const float ae = a + 1e-16f;
+    const float x = (ah - a) / ae;
+    if (x < -0.9999f) return fmaf(ae, logf(ae) - logf(ah + 1e-16f), ah - a);
+    return ae * (x - log1pf(x));
 }
 
 __global__ void __launch_bounds__(E_THREADS, 1)
@@ -150,48 +156,68 @@ k_error_tc(const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ 
         // ===================================== epilogue: TMEM tile of Ahat against the tile of A =====================================
         const int ew = warp - 2;
         const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
-        const int half = ew >> 2;                      // which 64 columns of the tile
+        const int part = ew >> 2;                      // which 32 columns of the tile
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         double acc_sq = 0.0, acc_kl = 0.0;
+        const float unscale = p.rsw[0] * p.rsh[0];
         uint32_t it = 0;
         for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
             const int64_t i = (t % p.tiles_i) * TM + quarter * 32 + lane;
-            const int64_t j0 = (t / p.tiles_i) * TN + half * 64;
+            const int64_t j0 = (t / p.tiles_i) * TN + part * 32;
             const uint32_t buf = it & 1, tph = (it >> 1) & 1;
             const bool row_ok = i < p.n;
-            const float ri = row_ok ? p.rsw[i] : 0.0f;
+            // this thread's 32 entries of A: every load is issued before the tile is waited for, so
+            // their latency hides behind the MMA (a first version loaded inside the compute loop, behind its branches: 64
+            // serialised L2 round trips per tile, 8 ms per evaluation instead of 0.5)
+            float av[32];
+#pragma unroll
+            for (int c = 0; c < 32; c++) {
+                const int64_t j = j0 + c;
+                const bool ok = row_ok && j < p.m;
+                av[c] = ok ? p.A[i + p.n * j] : __int_as_float(0x7fc00000);        // NaN = skipped like a missing entry
+            }
             mbar_wait(&tfull[buf], tph);
             tc_fence_after();
             float sq = 0.0f, kl = 0.0f;
 #pragma unroll
-            for (int ch = 0; ch < 2; ch++) {
-                uint32_t r0[32], r1[32];
-                const uint32_t t0 = tmem_base + lane_addr + buf * (2 * TN) + half * 64 + ch * 32;
-                TmemLd<32>::ld(t0, r0);
-                TmemLd<32>::ld(t0 + TN, r1);
+            for (int ch = 0; ch < 2; ch++) {           // two sub-chunks of 16 columns keep the TMEM read-out at 32 registers
+                uint32_t r0[16], r1[16];
+                const uint32_t t0 = tmem_base + lane_addr + buf * (2 * TN) + part * 32 + ch * 16;
+                TmemLd<16>::ld(t0, r0);
+                TmemLd<16>::ld(t0 + TN, r1);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (ch == 1) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[buf]);          // the MMA of the tile after next may overwrite this buffer
                 }
+                // branch-free main path (the series form of g; NaN from a missing entry flows through and is dropped by the
+                // final select), four independent accumulator pairs; entries outside the series' range are rare once the fit
+                // has started and are redone per thread with the general formula
+                float s4[4] = {0.f, 0.f, 0.f, 0.f}, k4[4] = {0.f, 0.f, 0.f, 0.f};
+                unsigned redo = 0;
 #pragma unroll
-                for (int c = 0; c < 32; c++) {
-                    const int64_t j = j0 + ch * 32 + c;
-                    if (row_ok && j < p.m) {
-                        const float a = p.A[i + p.n * j];
-                        if (((__float_as_uint(a) >> 23) & 0xffu) != 0xffu) {                  // finite: src/nnmf.cpp:124-125
-                            const float ah = fmaf(__uint_as_float(r1[c]), (float)LO_UNSCALE, __uint_as_float(r0[c])) * (ri * p.rsh[j]);
-                            const float r = a - ah;
-                            sq = fmaf(r, r, sq);
-                            const float ae = a + 1e-16f;
-                            const float x = __fdividef(ah - a, ae);
-                            // Ahat ~ 0 against a > 0 (x -> -1, beyond fp32's resolution of 1 + x): the same quantity written as
-                            // (a+e) log((a+e) / (Ahat+e)) + Ahat - a, which has no cancellation there
-                            kl += (x < -0.9999f) ? fmaf(ae, __logf(ae) - __logf(ah + 1e-16f), ah - a) : ae * g_of(x);
-                        }
-                    }
+                for (int c = 0; c < 16; c++) {
+                    const float a = av[ch * 16 + c];
+                    const bool fin = ((__float_as_uint(a) >> 23) & 0xffu) != 0xffu;            // finite: src/nnmf.cpp:124-125
+                    const float ah = fmaf(__uint_as_float(r1[c]), (float)LO_UNSCALE, __uint_as_float(r0[c])) * unscale;
+                    const float r = a - ah;
+                    const float ae = a + 1e-16f;
+                    const float x = __fdividef(ah - a, ae);
+                    const bool in_range = fabsf(x) < 0.125f;
+                    redo |= (fin && !in_range) ? (1u << c) : 0u;
+                    s4[c & 3] += fin ? r * r : 0.0f;
+                    k4[c & 3] += (fin && in_range) ? ae * g_series(x) : 0.0f;
                 }
+                if (redo) {
+#pragma unroll
+                    for (int c = 0; c < 16; c++)
+                        if ((redo >> c) & 1u)
+                            k4[0] += kl_term_general(av[ch * 16 + c],
+                                                     fmaf(__uint_as_float(r1[c]), (float)LO_UNSCALE, __uint_as_float(r0[c])) * unscale);
+                }
+                sq += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                kl += (k4[0] + k4[1]) + (k4[2] + k4[3]);
             }
             acc_sq += (double)sq;
             acc_kl += (double)kl;
@@ -215,28 +241,36 @@ k_error_tc(const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ 
     }
 }
 
-// X (k x cols, column-major fp64) -> planes [cols][KP] (row i = column i of X, zero beyond k), rs[i] = 1 / (power-of-two scale)
+// max |X| as a bit pattern (one atomicMax per block)
 __global__ void __launch_bounds__(256)
-k_split_rows(const double* __restrict__ X, int k, int64_t cols, int kp, __half* __restrict__ hi, __half* __restrict__ lo,
-             float* __restrict__ rs)
+k_absmax_bits(const double* __restrict__ X, int64_t total, unsigned long long* __restrict__ out)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;           // one warp per row
-    if (row >= cols) return;
-    double mx = 0.0;
-    for (int c = lane; c < k; c += 32) {
-        const double v = fabs(X[c + (int64_t)k * row]);
-        if (!is_missing(v)) mx = fmax(mx, v);
+    unsigned long long m = 0;
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+        const double v = fabs(X[e]);
+        if (!is_missing(v)) m = max(m, (unsigned long long)__double_as_longlong(v));
     }
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, s));
-    const double sc = pow2_scale(mx);
-    if (lane == 0) rs[row] = (float)(1.0 / sc);
-    for (int c = lane; c < kp; c += 32) {
+    for (int s = 16; s > 0; s >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, s));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// X (k x cols, column-major fp64) -> planes [cols][KP] (row i = column i of X, zero beyond k), scaled by the power of two that
+// brings max |X| into [2^13, 2^14); rs[0] = 1 / scale
+__global__ void __launch_bounds__(256)
+k_split_rows(const double* __restrict__ X, int k, int64_t cols, int kp, const unsigned long long* __restrict__ maxbits,
+             __half* __restrict__ hi, __half* __restrict__ lo, float* __restrict__ rs)
+{
+    const double sc = pow2_scale(__longlong_as_double((long long)maxbits[0]));
+    if (blockIdx.x == 0 && threadIdx.x == 0) rs[0] = (float)(1.0 / sc);
+    const int64_t total = cols * kp;
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < total; e += (int64_t)gridDim.x * 256) {
+        const int64_t row = e / kp;
+        const int c = (int)(e % kp);
         __half h = __float2half_rn(0.f), l = h;
         if (c < k) split2(X[c + (int64_t)k * row] * sc, h, l);
-        hi[row * kp + c] = h;
-        lo[row * kp + c] = l;
+        hi[e] = h;
+        lo[e] = l;
     }
 }
 
@@ -246,10 +280,16 @@ bool error_tc_supported(int k) { return k >= 1 && k <= 128; }
 int error_tc_kp(int k) { return k <= 64 ? 64 : 128; }
 int error_tc_grid(int64_t n, int64_t m) { return (int)std::min<int64_t>(sm_count(), ceil_div(n, TM) * ceil_div(m, TN)); }
 
-void launch_split_rows(const double* X, int k, int64_t cols, __half* hi, __half* lo, float* rs, cudaStream_t st)
+void launch_split_rows(const double* X, int k, int64_t cols, __half* hi, __half* lo, float* rs, unsigned long long* maxbits,
+                       cudaStream_t st)
 {
     if (cols <= 0) return;
-    k_split_rows<<<(unsigned)ceil_div(cols * 32, 256), 256, 0, st>>>(X, k, cols, error_tc_kp(k), hi, lo, rs);
+    const int64_t total = (int64_t)k * cols;
+    NNLM_CUDA_CHECK(cudaMemsetAsync(maxbits, 0, sizeof(unsigned long long), st));
+    k_absmax_bits<<<(int)std::min<int64_t>(ceil_div(total, 2048), 148 * 4), 256, 0, st>>>(X, total, maxbits);
+    NNLM_LAUNCHED();
+    const int kp = error_tc_kp(k);
+    k_split_rows<<<(int)std::min<int64_t>(ceil_div(cols * kp, 1024), 148 * 8), 256, 0, st>>>(X, k, cols, kp, maxbits, hi, lo, rs);
     NNLM_LAUNCHED();
 }
 

@@ -177,8 +177,9 @@ int64_t stats_part_count(int64_t cols);
 bool error_tc_supported(int k);
 int  error_tc_kp(int k);                       // padded rank of the row planes: 64 or 128
 int  error_tc_grid(int64_t n, int64_t m);      // CTAs = partial records
-// X (k x cols, column-major) -> fp16 planes [cols][kp] with one power-of-two scale per row; rs[i] = 1 / scale
-void launch_split_rows(const double* X, int k, int64_t cols, __half* hi, __half* lo, float* rs, cudaStream_t st);
+// X (k x cols, column-major) -> fp16 planes [cols][kp] under one power-of-two scale; rs[0] = 1 / scale; maxbits: one u64 of scratch
+void launch_split_rows(const double* X, int k, int64_t cols, __half* hi, __half* lo, float* rs, unsigned long long* maxbits,
+                       cudaStream_t st);
 // out[0] = sum (A - W'H)^2, out[1] = sum (A+e) g((W'H - A) / (A+e)) over the finite entries (see the file header)
 void launch_error_tc(const float* A, int64_t n, int64_t m, int k, const __half* w_hi, const __half* w_lo, const float* rsw,
                      const __half* h_hi, const __half* h_lo, const float* rsh, double* part, double* out, cudaStream_t st);

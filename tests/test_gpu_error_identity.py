@@ -111,3 +111,48 @@ def test_predict_mirrors_the_reference_method():
     np.testing.assert_allclose(pw.coefficients, refw.T, rtol=1e-7, atol=1e-10)
     with pytest.raises(ValueError):
         nnlm_b200.predict(r, newx[:-1], "H")
+
+
+@pytest.mark.parametrize("n,m,k,na", [(1000, 300, 6, 0.0), (2500, 1300, 50, 0.0), (1300, 700, 100, 0.0), (1500, 640, 20, 0.15)])
+def test_tensor_core_error_evaluation_matches_the_oracle(n, m, k, na):
+    """error_tc.cu (fast precision): mse and mkl of a mid-trajectory (W, H) from the tcgen05 tile of W'H folded against A in the
+    epilogue, vs the oracle's mse / mkl vectors and vs the fp64 pass of error_eval.cu (NNLM_ERR_FP64 not set here)."""
+    A = oracle.synth_matrix(n, m, min(k, 20), na_frac=na)
+    W0 = 0.01 * umat(11, n, k); H0 = 0.01 * umat(12, k, m)
+    ref = oracle.nnmf(A, k, W0, H0, max_iter=4, rel_tol=-1, n_threads=0, inner_max_iter=50, method=1, trace=1)
+    got = nnlm_b200.nnmf(A, k, init={"W": W0, "H": H0}, max_iter=4, rel_tol=-1, trace=1, show_warning=False, check_k=False,
+                         precision=K.PREC_FAST)
+    exact = nnlm_b200.nnmf(A, k, init={"W": W0, "H": H0}, max_iter=4, rel_tol=-1, trace=1, show_warning=False, check_k=False,
+                           precision=K.PREC_EXACT)
+    print(f"{n}x{m} k={k} na={na}: mse rel {np.abs(got.mse / ref['mse'] - 1).max():.1e}, mkl rel {np.abs(got.mkl / ref['mkl'] - 1).max():.1e} "
+          f"(fp64 pass: {np.abs(exact.mse / ref['mse'] - 1).max():.1e}, {np.abs(exact.mkl / ref['mkl'] - 1).max():.1e})")
+    # k = 100 over a rank-20 matrix: the trajectory itself is chaotic from the second iteration on (DESIGN.md §2; the fp64 path
+    # drifts from the oracle just the same), so only the first record isolates the evaluation there
+    upto = 1 if k > 50 else len(ref["mse"])
+    np.testing.assert_allclose(got.mse[:upto], ref["mse"][:upto], rtol=2e-6)
+    np.testing.assert_allclose(got.mkl[:upto], ref["mkl"][:upto], rtol=2e-6)
+    np.testing.assert_allclose(got.target_loss[:upto], ref["target_loss"][:upto], rtol=2e-6)
+    # and the two evaluations agree on the SAME factors: the fp64 pass on the fast path's final (W, H)
+    with Session(A, k=k, method=1, precision=K.PREC_FAST) as s:
+        s.set_factors(got.W, got.H)
+        mse_tc, mkl_tc, _ = s.error()
+    with Session(A, k=k, method=1, precision=K.PREC_EXACT) as s:
+        s.set_factors(got.W, got.H)
+        mse_64, mkl_64, _ = s.error()
+    assert abs(mse_tc / mse_64 - 1) < 2e-6 and abs(mkl_tc / mkl_64 - 1) < 2e-6, (mse_tc, mse_64, mkl_tc, mkl_64)
+
+
+def test_tensor_core_error_with_vanishing_reconstruction():
+    """Entries where W'H is exactly 0 against a > 0 (masked-out factors): the KL term stays finite and equal to the reference's
+    -(a+e) log(0+e) (src/nnmf.cpp:139), through the branch that avoids 1 + x in fp32."""
+    n, m, k = 700, 260, 4
+    A = oracle.synth_matrix(n, m, k)
+    W0 = 0.01 * umat(11, n, k); H0 = 0.01 * umat(12, k, m)
+    Hm = np.zeros((k, m), dtype=bool); Hm[:, :7] = True          # seven columns of H pinned to zero -> Ahat = 0 there
+    H0[Hm] = 0
+    ref = oracle.nnmf(A, k, W0, H0, Hm=Hm, max_iter=3, rel_tol=-1, n_threads=0, inner_max_iter=50, method=1, trace=1)
+    got = nnlm_b200.nnmf(A, k, init={"W": W0, "H": H0}, mask={"H": Hm}, max_iter=3, rel_tol=-1, trace=1, show_warning=False,
+                         check_k=False, precision=K.PREC_FAST)
+    assert np.isfinite(got.mkl).all()
+    np.testing.assert_allclose(got.mkl, ref["mkl"], rtol=1e-5)
+    np.testing.assert_allclose(got.mse, ref["mse"], rtol=2e-6)

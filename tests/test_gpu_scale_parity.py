@@ -215,3 +215,20 @@ def test_auto_precision_takes_the_tensor_core_path_on_ordinary_data():
                              show_warning=False, precision=K.PREC_AUTO)
         assert got.stats["precision_used"] == K.PREC_FAST
         assert rel(got.W, ref["W"]) < TOL and rel(got.H, ref["H"]) < TOL
+
+
+def test_config5_sixteenth_subproblem():
+    """BASELINE config 5 (200000 x 20000, k = 128) cannot be held by the CPU oracle (32 GB + its transpose); SURVEY.md §8d asks
+    for oracle parity on a 1/16 sub-problem: 25000 x 10000, k = 128, T = 1 from the BASELINE init, through the config-5
+    instantiations k_cross_tc<128,3> (128-index TMEM drain) + k_scd_chain<32,1>. bench.py --config 5 carries the N-GPU vs
+    1-GPU check of the full size in its `parity` field."""
+    n, m, k = 25000, 10000, 128
+    A = synth(n, m, k)
+    W0 = 0.01 * umat(11, n, k); H0 = 0.01 * umat(12, k, m)
+    ref = oracle.nnmf(A, k, W0, H0, max_iter=1, rel_tol=-1, n_threads=0, inner_max_iter=50, method=1, trace=1)
+    got = nnlm_b200.nnmf(A, k, init={"W": W0, "H": H0}, max_iter=1, rel_tol=-1, trace=1, inner_max_iter=50, check_k=False,
+                         show_warning=False, precision=K.PREC_FAST)
+    ew, eh = rel(got.W, ref["W"]), rel(got.H, ref["H"])
+    print(f"config 5 / 16 ({n}x{m}, k={k}) T=1: rel W {ew:.2e}, rel H {eh:.2e}; mse {got.mse} / {ref['mse']}")
+    assert ew < TOL and eh < TOL
+    np.testing.assert_allclose(got.mse, ref["mse"], rtol=2e-6)
