@@ -220,8 +220,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--precision", type=int, default=2, help="1 exact (fp64 A), 2 fast")
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json configuration (default: the headline)")
+    ap.add_argument("--shape", default="", help="n,m,k: override the problem size (experiments; not a bench line)")
     args = ap.parse_args()
     wl = workload(args.small, args.config)
+    if args.shape:
+        wl["n"], wl["m"], wl["k"] = (int(x) for x in args.shape.split(","))
+        wl["name"] = f"custom {wl['n']}x{wl['m']}, k={wl['k']} (experiment)"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -430,7 +434,9 @@ def main():
             extra = {"calls_s": [w for w, _ in runs], "upload_ms": r.stats["upload_ms"], "loop_ms": r.stats["loop_ms"],
                      "download_ms": r.stats["download_ms"], "host_setup_ms": r.stats["host_setup_ms"],
                      "host_loop_ms": r.stats["host_loop_ms"], "host_finish_ms": r.stats["host_finish_ms"],
-                     "host_total_ms": r.stats["host_total_ms"], "python_run_time_s": r.run_time}
+                     "host_total_ms": r.stats["host_total_ms"], "host_alloc_ms": r.stats["host_alloc_ms"],
+                     "host_teardown_ms": r.stats["host_teardown_ms"], "python_run_time_s": r.run_time,
+                     "per_call": [{k2: rr.stats[k2] for k2 in ("host_setup_ms", "host_loop_ms", "host_alloc_ms", "host_teardown_ms", "host_total_ms")} for _, rr in runs]}
             if long_T:
                 wl200, _ = call(long_T)
                 extra["at_200_steps"] = {"value": long_T / wl200, "seconds": wl200}

@@ -116,6 +116,8 @@ typedef struct nnlm_stats {
     double host_total_ms;     /* host wall clock from entry to just before return (set-up + loop + finish + teardown) */
     int32_t n_gpus_used;      /* devices this call ran on                                           */
     int32_t mse_from_identity;/* 1 = the traced MSE came from ||A||^2 - 2<H,WtA> + <WtW,HHt> (no pass over A) */
+    double host_alloc_ms;     /* host wall clock inside device allocations (cudaMallocAsync + sync) during the call */
+    double host_teardown_ms;  /* host wall clock releasing the call's device state                                 */
 } nnlm_stats;
 
 /* ---- c_nnmf (src/nnmf.cpp:4-220) -------------------------------------------------------------

@@ -37,7 +37,8 @@ class Stats(C.Structure):
                 ("gram_ms", C.c_double), ("cross_launches", C.c_uint64), ("solve_launches", C.c_uint64),
                 ("comm_ms", C.c_double), ("comm_bytes", C.c_uint64),
                 ("host_setup_ms", C.c_double), ("host_loop_ms", C.c_double), ("host_finish_ms", C.c_double),
-                ("host_total_ms", C.c_double), ("n_gpus_used", C.c_int32), ("mse_from_identity", C.c_int32)]
+                ("host_total_ms", C.c_double), ("n_gpus_used", C.c_int32), ("mse_from_identity", C.c_int32),
+                ("host_alloc_ms", C.c_double), ("host_teardown_ms", C.c_double)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_ if not f.startswith("reserved")}

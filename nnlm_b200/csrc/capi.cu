@@ -282,6 +282,10 @@ int nnmf_single(const NnmfCall& c, std::chrono::steady_clock::time_point t_entry
 {
     const int dev = device_of(c.opt);
     ScopedDevice sd(dev);
+    const double alloc0 = alloc_ms_counter();
+    int rc = NNLM_OK;
+    std::chrono::steady_clock::time_point t_done;
+    {
     Engine eng(c.n, c.m, c.K, c.method, c.precision, dev);
     eng.timer.enable(c.opt && c.opt->verbose_timing);
     Events ev;
@@ -293,8 +297,16 @@ int nnmf_single(const NnmfCall& c, std::chrono::steady_clock::time_point t_entry
     eng.set_inner(c.inner_max_iter, c.inner_rel_tol);
     ev.record(1, eng.stream());
     eng.sync();
-    const int rc = anls_loop(eng, c, true, nullptr, t_entry, launches0);
+    rc = anls_loop(eng, c, true, nullptr, t_entry, launches0);
     if (c.stats && rc == NNLM_OK) { c.stats->upload_ms = elapsed(ev.e[0], ev.e[1]); c.stats->n_gpus_used = 1; }
+    t_done = std::chrono::steady_clock::now();
+    }   // the engine and its device buffers go here
+    if (std::getenv("NNLM_B200_TRACE"))
+        std::fprintf(stderr, "[nnlm_b200] teardown: cudaFreeAsync %.1f ms, pinned alloc/free %.1f ms (thread totals)\n", free_ms_counter(), pinned_ms_counter());
+    if (c.stats && rc == NNLM_OK) {
+        c.stats->host_alloc_ms = alloc_ms_counter() - alloc0;
+        c.stats->host_teardown_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_done).count();
+    }
     return rc;
 }
 

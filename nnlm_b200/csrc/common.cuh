@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -63,6 +64,16 @@ inline void pool_setup_once()
     done_for = dev;
 }
 
+// host wall clock spent inside cudaMallocAsync (+ its synchronisation) on this thread: nnlm_stats.host_alloc_ms
+inline double& alloc_ms_counter() { static thread_local double ms = 0.0; return ms; }
+inline double& free_ms_counter() { static thread_local double ms = 0.0; return ms; }          // cudaFreeAsync
+inline double& pinned_ms_counter() { static thread_local double ms = 0.0; return ms; }        // cudaMallocHost / cudaFreeHost
+struct ScopedMs {
+    double& acc; std::chrono::steady_clock::time_point t0;
+    explicit ScopedMs(double& a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+    ~ScopedMs() { acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 // RAII device allocation
 template <typename T>
 struct DevBuf {
@@ -82,12 +93,14 @@ struct DevBuf {
         release();
         if (n == 0) return;
         pool_setup_once();
+        const auto t0 = std::chrono::steady_clock::now();
         NNLM_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&p), n * sizeof(T), (cudaStream_t)0));
         NNLM_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)0));      // usable from any stream from here on
+        alloc_ms_counter() += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         count = n;
     }
     void ensure(size_t n) { if (n > count) alloc(n); }
-    void release() { if (p) { cudaFreeAsync(p, (cudaStream_t)0); p = nullptr; count = 0; } }
+    void release() { if (p) { ScopedMs t(free_ms_counter()); cudaFreeAsync(p, (cudaStream_t)0); p = nullptr; count = 0; } }
     size_t bytes() const { return count * sizeof(T); }
     explicit operator bool() const { return p != nullptr; }
 };
@@ -103,11 +116,12 @@ struct PinnedBuf {
     void alloc(size_t n) {
         release();
         if (n == 0) return;
+        ScopedMs t(pinned_ms_counter());
         NNLM_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&p), n * sizeof(T)));
         count = n;
     }
     void ensure(size_t n) { if (n > count) alloc(n); }
-    void release() { if (p) { cudaFreeHost(p); p = nullptr; count = 0; } }
+    void release() { if (p) { ScopedMs t(pinned_ms_counter()); cudaFreeHost(p); p = nullptr; count = 0; } }
 };
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -44,11 +44,12 @@ constexpr int BK = 64;           // fp16 elements per k-block (128 bytes)
 // k-blocks accumulated in TMEM between two drains into the fp64 registers. The fp32 accumulation in TMEM is the dominant error
 // of the whole cross-product (measured, 5000 x 2000, contraction length 2000: relative Frobenius error 6.4e-10 / 3.5e-10 /
 // 2.0e-10 / 1.5e-10 at 16 / 4 / 2 / 1 k-blocks per drain); the epilogue hides behind the HBM stream down to 4 k-blocks for the
-// 32- and 64-row factor tiles (cross-product time +0.9 %), and costs 24 % at 2 k-blocks for the 128-row tile, where it buys
-// the 1e-5 parity of the first iteration at k = 128 (the near-rank-one tiny init amplifies the W-half's error ~2000x into H:
-// tests/test_gpu_scale_parity.py, profiles/r2_b_drain_interval.md).
+// 32- and 64-row factor tiles (cross-product time +0.9 %); the 128-row tile drains every k-block, which buys the 1e-5 parity of
+// the first iteration at k = 128 (the near-rank-one tiny init amplifies the W-half's error ~2000x into H:
+// tests/test_gpu_scale_parity.py, profiles/r2_b_drain_interval.md). Only the hi*hi accumulator is drained that often; the
+// small-term accumulator (2^-11 of it) keeps 16 k-blocks per drain, which halves the epilogue's conversions.
 constexpr int DRAIN_SMALL = 4;    // NP = 32, 64: 256 contraction indices
-constexpr int DRAIN_LARGE = 2;    // NP = 128:    128 contraction indices
+constexpr int DRAIN_LARGE = 1;    // NP = 128:     64 contraction indices
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 32 * (2 + EPI_WARPS);
 
@@ -60,6 +61,7 @@ struct CrossParams {
     double* Qp;            // [slots][ncol][k]
     const double* unscale; // [NP]: 1 / (s_A * s_F[a])
     int drain;             // k-blocks accumulated in TMEM between two drains into the fp64 registers
+    int d1_every;          // drains of the large-term accumulator per drain of the small-term one (MODE 0; 1 otherwise)
     const double* center;  // [ncol] mean of each column of A that was subtracted before the split (or nullptr)
     const double* fsum;    // [k] row sums of the factor
 };
@@ -146,16 +148,23 @@ k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             uint32_t chunk = 0;                       // running drain-chunk counter of this CTA
+            uint32_t big = 0, cur_big = 0;            // MODE 0: the small-term accumulator d1 is drained once per p.d1_every chunks
             int64_t u = u0;
             while (u < u1) {
                 const int64_t tile = u / KBn;
                 const int64_t seg_end = min(u1, (tile + 1) * KBn);
+                uint32_t sub = 0;
                 while (u < seg_end) {
                     const int64_t chunk_end = min(seg_end, u + (int64_t)p.drain);
                     const uint32_t buf = chunk & 1, tph = (chunk >> 1) & 1;
                     mbar_wait(&tempty[buf], tph ^ 1);           // epilogue has drained this TMEM buffer
                     tc_fence_after();
-                    const uint32_t d0 = tmem_base + buf * (2 * NP), d1 = d0 + NP;
+                    const bool big_first = (sub % (uint32_t)p.d1_every) == 0;
+                    if (big_first) cur_big = big++;
+                    // TMEM: d0[2] at columns [0, 2 NP), d1[2] at [2 NP, 4 NP). The d1 buffer of big chunk B is free again when B+2
+                    // starts: the tempty wait above covers the drain chunk two before this one, which is at or after the last
+                    // chunk of B (B+1 holds at least one chunk), and the epilogue reads d1 before it arrives on that chunk.
+                    const uint32_t d0 = tmem_base + buf * NP, d1 = tmem_base + 2 * NP + (cur_big & 1) * NP;
                     bool first = true;
                     for (; u < chunk_end; u++) {
                         mbar_wait(&full[stage], phase);
@@ -168,8 +177,9 @@ k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ 
                         for (int ks = 0; ks < BK / 16; ks++) {
                             const uint64_t adv = (uint64_t)((ks * 32) >> 4);     // 16 fp16 = 32 bytes along K
                             const uint32_t acc = (first && ks == 0) ? 0u : 1u;
+                            const uint32_t acc1 = (first && ks == 0 && big_first) ? 0u : 1u;
                             umma_f16(d0, a_hi + adv, f_hi + adv, IDESC, acc);    // hi*hi
-                            if (MODE != 1) umma_f16(d1, a_hi + adv, f_lo + adv, IDESC, acc);    // hi*lo (MODE 2: the next slice)
+                            if (MODE != 1) umma_f16(d1, a_hi + adv, f_lo + adv, IDESC, acc1);   // hi*lo (MODE 2: the next slice)
                             if (MODE == 0) umma_f16(d1, a_lo + adv, f_hi + adv, IDESC, 1u);      // lo*hi
                         }
                         first = false;
@@ -178,6 +188,7 @@ k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ 
                     }
                     tc_commit(&tfull[buf]);                     // accumulators of this chunk are complete
                     chunk++;
+                    sub++;
                 }
             }
         }
@@ -188,7 +199,7 @@ k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ 
         const int half = ew >> 2;                     // which half of the NP accumulator columns
         const int row = quarter * 32 + lane;          // row of the tile = column of A
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-        uint32_t chunk = 0;
+        uint32_t chunk = 0, big = 0, cur_big = 0;
         int64_t u = u0;
         while (u < u1) {
             const int64_t tile = u / KBn;
@@ -196,31 +207,43 @@ k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ 
             double acc[CPT];
 #pragma unroll
             for (int c = 0; c < CPT; c++) acc[c] = 0.0;
+            uint32_t sub = 0;
             while (u < seg_end) {
                 const int64_t chunk_end = min(seg_end, u + (int64_t)p.drain);
                 const uint32_t buf = chunk & 1, tph = (chunk >> 1) & 1;
+                if ((sub % (uint32_t)p.d1_every) == 0) cur_big = big++;
+                // the small-term accumulator is read with the last drain chunk of its group (or of the tile)
+                const bool with_d1 = MODE != 1 && (chunk_end == seg_end || ((sub + 1) % (uint32_t)p.d1_every) == 0);
                 mbar_wait(&tfull[buf], tph);
                 tc_fence_after();
                 constexpr int CH = CPT > 32 ? 32 : CPT;          // TMEM columns read per tcgen05.ld
-                const uint32_t t0 = tmem_base + lane_addr + buf * (2 * NP) + half * CPT;
+                const uint32_t t0 = tmem_base + lane_addr + buf * NP + half * CPT;
+                const uint32_t t1 = tmem_base + lane_addr + 2 * NP + (cur_big & 1) * NP + half * CPT;
+                // one read-out array live at a time (the 128-row tile has 64 fp64 accumulators per thread already)
 #pragma unroll
                 for (int ch = 0; ch < CPT / CH; ch++) {
-                    uint32_t r0[CH], r1[CH];
-                    TmemLd<CH>::ld(t0 + ch * CH, r0);
-                    if (MODE != 1) TmemLd<CH>::ld(t0 + NP + ch * CH, r1);
+                    uint32_t r[CH];
+                    TmemLd<CH>::ld(t0 + ch * CH, r);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (ch == CPT / CH - 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty[buf]);   // buffer may be overwritten by the next-but-one chunk
-                    }
 #pragma unroll
-                    for (int c = 0; c < CH; c++)
-                        acc[ch * CH + c] += MODE != 1 ? (double)__uint_as_float(r0[c]) + (double)__uint_as_float(r1[c]) * LO_UNSCALE
-                                                      : (double)__uint_as_float(r0[c]);
+                    for (int c = 0; c < CH; c++) acc[ch * CH + c] += (double)__uint_as_float(r[c]);
                 }
+                if (with_d1) {
+#pragma unroll
+                    for (int ch = 0; ch < CPT / CH; ch++) {
+                        uint32_t r[CH];
+                        TmemLd<CH>::ld(t1 + ch * CH, r);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int c = 0; c < CH; c++) acc[ch * CH + c] = fma((double)__uint_as_float(r[c]), LO_UNSCALE, acc[ch * CH + c]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[buf]);           // buffer may be overwritten by the next-but-one chunk
                 u = chunk_end;
                 chunk++;
+                sub++;
             }
             // partial tile -> slot (index of this CTA among the CTAs that touch the tile)
             const int64_t slot = (int64_t)blockIdx.x - first_cta_of_unit(tile * KBn, U, P);
@@ -406,6 +429,9 @@ void launch_np(const CrossPlan& plan, const __half* a_hi, const __half* a_lo, co
     p.ncol = plan.ncol; p.kblocks = plan.kblocks; p.units = plan.units; p.k = plan.k; p.Qp = Qp; p.unscale = unscale;
     static const int drain_env = [] { const char* e = getenv("NNLM_TC_DRAIN"); return e ? atoi(e) : 0; }();
     p.drain = drain > 0 ? drain : (drain_env > 0 ? drain_env : (NP >= 128 ? DRAIN_LARGE : DRAIN_SMALL));
+    // the hi*lo + lo*hi accumulator is 2^-11 of the hi*hi one: its fp32 truncation matters 2^-11 as much, so it keeps
+    // round 1's 1024 indices per drain and the epilogue converts half as many values on the other drains
+    p.d1_every = MODE == 0 ? std::max(1, 16 / p.drain) : 1;
     p.center = center; p.fsum = fsum;
     NNLM_CUDA_CHECK(cudaMemsetAsync(Qp, 0, sizeof(double) * (size_t)plan.slots * plan.ncol * plan.k, st));
     kern<<<plan.grid, THREADS, smem, st>>>(mA_hi, mA_lo, mF_hi, mF_lo, p);

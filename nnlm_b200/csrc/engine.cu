@@ -3,12 +3,15 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
 namespace nnlm {
 
 namespace {
+constexpr int SCD_WARP_MAX_COLS = 0;      // columns per launch up to which the warp-per-column SCD solver is used (measured: see solve_dense_ls)
 struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (dev >= 0 && dev != prev) cudaSetDevice(dev); }
@@ -90,10 +93,17 @@ Engine::Engine(int64_t n, int64_t m, int k, int method, int precision, int devic
 
 Engine::~Engine()
 {
+    const bool trace = std::getenv("NNLM_B200_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    const auto t0 = now();
     if (st2_) { cudaStreamSynchronize(st2_); cudaStreamDestroy(st2_); }
     if (st_) { cudaStreamSynchronize(st_); cudaStreamDestroy(st_); }
+    const auto t1 = now();
     if (ev_fork_) cudaEventDestroy(ev_fork_);
     if (ev_join_) cudaEventDestroy(ev_join_);
+    if (trace)
+        std::fprintf(stderr, "[nnlm_b200] ~Engine: streams %.1f ms, events %.1f ms (buffers are released after this)\n",
+                     std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(now() - t1).count());
 }
 
 void Engine::ensure_scratch()
@@ -129,7 +139,6 @@ void Engine::ensure_scratch()
     tpc_scratch_.alloc(scd_tpc_scratch_doubles());      // [0]: the solver's group counter, [1]: the ticket of k_factor_prep
     NNLM_CUDA_CHECK(cudaMemsetAsync(tpc_scratch_.p, 0, tpc_scratch_.bytes(), st_));
     sweeps_.alloc(1);
-    host_small_.alloc(16);
     NNLM_CUDA_CHECK(cudaMemsetAsync(sweeps_.p, 0, sizeof(unsigned long long), st_));
 }
 
@@ -373,7 +382,11 @@ void Engine::solve_dense_ls(const Half& h, int splits)
     join_gram();
     timer.begin(KernelTimer::SOLVE, st_);
     if (h.ncol > 0) {
-        if (method_ == 1 && scd_tpc_supported(k_))
+        // Few columns (small shards of the multi-GPU path): the blocked DMMA solver is bound by the latency of ONE tile
+        // (350 blocks of ~1650 cycles however few tiles there are), the warp-per-column solver by 2500 dependent steps of
+        // ~60 cycles per sweep set but with every column in flight at once: below the measured switch point it wins.
+        static const int64_t warp_max = [] { const char* e = std::getenv("NNLM_SCD_WARP_MAX"); return e ? atoll(e) : (int64_t)SCD_WARP_MAX_COLS; }();
+        if (method_ == 1 && scd_tpc_supported(k_) && h.ncol > warp_max)
             launch_scd_tpc(h.X, G_.p, Qp_.p, splits, h.mask, k_, h.ncol, h.pen[2], inner_max_iter_, inner_rel_tol_, sweeps_.p,
                            tpc_scratch_.p, st_);
         else

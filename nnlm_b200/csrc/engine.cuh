@@ -182,7 +182,10 @@ private:
     // scratch
     DevBuf<double> gram_part_, rowsum_part_, G_, Graw_, G2_, sumY_, Qp_, Yr_, wh_, red_part_, small_, tpc_scratch_;   // small_: 16 doubles of results
     DevBuf<unsigned long long> sweeps_;
-    PinnedBuf<double> host_small_;
+    // read-back area of the few scalars a call returns (sums, counters). Plain host memory on purpose: cudaMallocHost /
+    // cudaFreeHost of even 128 bytes took up to 600 ms per call next to large pinned regions of the host program
+    // (scratch/e2e_probe.py, the e2e variance of round 1); every read-back is followed by a stream synchronisation anyway.
+    struct HostSmall { double v[16]; double* p = v; } host_small_;
 };
 
 }  // namespace nnlm

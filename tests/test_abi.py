@@ -39,7 +39,7 @@ def test_struct_layouts_match_header():
     lib = K.lib()
     lib.nnlm_sizeof.restype = C.c_size_t
     assert C.sizeof(K.Options) == lib.nnlm_sizeof(0) == 48
-    assert C.sizeof(K.Stats) == lib.nnlm_sizeof(1) == 160
+    assert C.sizeof(K.Stats) == lib.nnlm_sizeof(1) == 176
 
 
 def test_no_cpu_fallback():
