@@ -49,6 +49,15 @@ __device__ __forceinline__ float fast_div(float a, float w)
     return a * r;
 }
 
+__device__ __forceinline__ float fast_div_newton(float a, float w)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(w));
+    r = fmaf(fmaf(-w, r, 1.0f), r, r);
+    const float q = a * r;
+    return fmaf(fmaf(-w, q, a), r, q);           // correctly rounded quotient up to one ulp
+}
+
 // sums of NV per-lane values over the warp with NV - 1 + log2(32 / NV) shuffles instead of 5 NV: lanes trade halves of their
 // value vector on the way down (fp32; the totals cross warps, CTAs and coordinates in fp64). Result for value x ends in lane
 // (x * 32 / NV) ... returned as: every lane holds the total of value (lane / (32 / NV)).
@@ -124,6 +133,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     } while (!done);
 }
 
+// number of doubles at the head of the dynamic shared memory (hs, sw, red, xch, 2 mbarriers), rounded up to an even count
+__host__ __device__ constexpr size_t klf_head_doubles(int k)
+{
+    return (((size_t)KLF_J * k + k + KLF_NW * KLF_NV + 2 * KLF_MAXS * KLF_NV + 2) + 1) & ~(size_t)1;
+}
+__device__ __forceinline__ unsigned char* sm_doubles_end(unsigned char* base, int k) { return base + sizeof(double) * klf_head_doubles(k); }
+
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int METHOD, int E>
@@ -143,7 +159,8 @@ k_solve_kl_fast(double* __restrict__ X, const float* __restrict__ Y32, const flo
     double* red = sw + k;                                        // [KLF_NW][KLF_NV]
     double* xch = red + KLF_NW * KLF_NV;                         // [2][KLF_MAXS][KLF_NV] records of every CTA of the cluster
     uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 2 * KLF_MAXS * KLF_NV);   // [2] one mbarrier per exchange buffer
-    float* dS = reinterpret_cast<float*>(bars + 2);              // [KLF_J] step d of the coordinate just solved; [KLF_J] = "another sweep" flag
+    // (the double section is padded to an even count so the float4 tile of A below stays 16-byte aligned for every k)
+    float* dS = reinterpret_cast<float*>(sm_doubles_end(smem_raw, k));   // [KLF_J] step d of the coordinate just solved; [KLF_J] = "another sweep" flag
     float* aS = dS + 2 * KLF_J;                                  // [E][KLF_J][KLF_NT] this thread's entries of A
     float* yS = aS + (size_t)E * KLF_J * KLF_NT;                 // [2][E][KLF_NT] this thread's entries of two factor rows
 
@@ -264,9 +281,13 @@ k_solve_kl_fast(double* __restrict__ X, const float* __restrict__ Y32, const flo
                         wh[e][j] = w;
                         const float a = av[j];
                         if (METHOD == 3) {
-                            const float mu = fast_div(y, w + 1e-16f);                 // :97
+                            const float we = w + 1e-16f;
+                            const float mu = fast_div_newton(y, we);                  // :97
                             pa[j] = fmaf(a * mu, mu, pa[j]);                          // dot(Aj, square(mu))
-                            pb[j] = fmaf(a, mu, pb[j]);                               // dot(Aj, mu)
+                            // the reference forms dot(Aj, mu) - sumW(k) (:99), two sums that cancel to the size of the gradient;
+                            // with sumW(k) = sum_i y_i and y_i = mu_i (wh_i + eps) the difference is sum_i (A_i - wh_i - eps) mu_i,
+                            // accumulated here entry by entry so that fp32 keeps its relative precision on the small result
+                            pb[j] = fmaf(a - we, mu, pb[j]);
                         } else {
                             pa[j] = fmaf(y, fast_div(a, w + 1e-16f), pa[j]);          // dot(Wt.row(c), Aj / (wh + eps))  (:141)
                         }
@@ -292,15 +313,22 @@ k_solve_kl_fast(double* __restrict__ X, const float* __restrict__ Y32, const flo
                 const uint32_t buf = step & 1;
                 double* mine = xch + buf * KLF_MAXS * KLF_NV;
                 if (warp == 0) {
-                    if (lane == 0) mbar_arrive_expect_tx(bar_s + 8 * buf, (uint32_t)(S * NVM * 8));
+                    double s = 0.0;
                     if (lane < NVM) {
-                        double s = 0.0;
 #pragma unroll
                         for (int w2 = 0; w2 < KLF_NW; w2++) s += red[w2 * KLF_NV + lane];
-                        const uint32_t slot = xch_s + 8u * (buf * KLF_MAXS * KLF_NV + rank * KLF_NV + lane);
-                        for (int r = 0; r < S; r++) st_async_f64(map_to_rank(slot, r), s, map_to_rank(bar_s + 8 * buf, r));
                     }
-                    mbar_wait_cluster(bar_s + 8 * buf, (step >> 1) & 1);
+                    if (S == 1) {                      // a single CTA: the record stays local, no distributed shared memory involved
+                        if (lane < NVM) mine[lane] = s;
+                        __syncwarp();
+                    } else {
+                        if (lane == 0) mbar_arrive_expect_tx(bar_s + 8 * buf, (uint32_t)(S * NVM * 8));
+                        if (lane < NVM) {
+                            const uint32_t slot = xch_s + 8u * (buf * KLF_MAXS * KLF_NV + rank * KLF_NV + lane);
+                            for (int r = 0; r < S; r++) st_async_f64(map_to_rank(slot, r), s, map_to_rank(bar_s + 8 * buf, r));
+                        }
+                        mbar_wait_cluster(bar_s + 8 * buf, (step >> 1) & 1);
+                    }
                 }
                 // ---- the update of coordinate c: lane j of warp 0 owns column j (every CTA computes the same numbers) ----
                 if (warp == 0 && lane < KLF_J) {
@@ -313,7 +341,7 @@ k_solve_kl_fast(double* __restrict__ X, const float* __restrict__ Y32, const flo
                         const double hc = hs[j * k + c];
                         double hn = hc;
                         if (METHOD == 3) {
-                            double a2 = ta, b = tb - sw[c];
+                            double a2 = ta, b = tb;                                   // tb = dot(Aj, mu) - sumW(c), see the pass
                             a2 += b0;                                                 // :100 (before a*h, as in the code)
                             b += a2 * hc - b2 - b1 * (sumH - hc);
                             double cand = b / (a2 + tiny);
@@ -372,7 +400,7 @@ k_solve_kl_fast(double* __restrict__ X, const float* __restrict__ Y32, const flo
 
 inline size_t klf_smem(int k, int e)
 {
-    return sizeof(double) * ((size_t)KLF_J * k + k + KLF_NW * KLF_NV + 2 * KLF_MAXS * KLF_NV + 2)
+    return sizeof(double) * klf_head_doubles(k)
          + sizeof(float) * (2 * KLF_J + (size_t)e * KLF_J * KLF_NT + 2 * (size_t)e * KLF_NT);
 }
 

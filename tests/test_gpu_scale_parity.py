@@ -232,3 +232,27 @@ def test_config5_sixteenth_subproblem():
     print(f"config 5 / 16 ({n}x{m}, k={k}) T=1: rel W {ew:.2e}, rel H {eh:.2e}; mse {got.mse} / {ref['mse']}")
     assert ew < TOL and eh < TOL
     np.testing.assert_allclose(got.mse, ref["mse"], rtol=2e-6)
+
+
+@pytest.mark.parametrize("k", [1, 5, 9, 33])
+@pytest.mark.parametrize("method,inner", [(4, 1), (3, 2)])
+def test_kl_fast_path_odd_ranks(method, inner, k):
+    """The cluster KL solver stages A as float4 in shared memory behind a k-dependent block of doubles: compute-sanitizer found
+    the tile misaligned for odd k (round 2); every parity of k and both cluster shapes (len 1300 -> 1 CTA, 5000 -> 2) are run."""
+    n, m = 5000, 1300
+    A = synth(n, m, max(k, 2))
+    W0 = 0.01 * umat(11, n, k) + 0.01; H0 = 0.01 * umat(12, k, m) + 0.01
+    kw = dict(max_iter=2, rel_tol=-1, n_threads=0, inner_max_iter=inner, method=method, trace=1)
+    ref = oracle.nnmf(A, k, W0, H0, **kw)
+    # the oracle's own answer to an init perturbed by 1e-9 (relative): the fp32 ratios of the fast path perturb at ~1e-7
+    rng = np.random.default_rng(1)
+    pert = oracle.nnmf(A, k, W0 * (1 + 1e-9 * rng.standard_normal(W0.shape)), H0 * (1 + 1e-9 * rng.standard_normal(H0.shape)), **kw)
+    amp = max(rel(pert["W"], ref["W"]), rel(pert["H"], ref["H"])) / 1e-9
+    got = nnlm_b200.nnmf(A, k, method="scd" if method == 3 else "lee", loss="mkl", init={"W": W0, "H": H0}, max_iter=2, rel_tol=-1,
+                         trace=1, inner_max_iter=inner, check_k=False, show_warning=False, precision=K.PREC_FAST)
+    ew, eh = rel(got.W, ref["W"]), rel(got.H, ref["H"])
+    print(f"KL fast k={k} method={method}: rel W {ew:.2e}, rel H {eh:.2e}; oracle amplification of a 1e-9 perturbation: {amp:.1f}x; "
+          f"mkl {got.mkl} / {ref['mkl']}")
+    bar = max(TOL, 3e-7 * amp)
+    assert ew < bar and eh < bar
+    np.testing.assert_allclose(got.mkl, ref["mkl"], rtol=max(1e-5, 3e-7 * amp))
