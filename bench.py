@@ -364,6 +364,24 @@ def main():
                     "hbm_side": {"achieved": mask_bytes / t / 1e9 if t > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
                                  "bytes_per_step": mask_bytes, "what": "fp16 mask plane streamed once per launch (the two slice planes of Z come from L2: 2x these bytes)"},
                     "solve_ms_per_step": st["solve_ms"] / args.steps}
+    # DRAM traffic per launch of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum from the `ncu --set full`
+    # captures summarised in profiles/r2_traffic.json (a citation of those captures, valid for the full-size single-GPU
+    # configurations they were taken on; null elsewhere)
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        if world == 1 and not args.small and not args.shape:
+            pick = {2: ["k_scd_chain<13, 2>", "k_scd_chain<13, 1>"], 5: [], 3: ["k_solve_kl_fast<4, 10>", "k_solve_kl_fast<4, 13>"],
+                    4: ["k_cross_tc<128, 4, 2>"]}[args.config]
+            vals = [v for kname in pick for v in tj.get(f"config{args.config}", {}).get(kname, {}).get("dram_bytes_per_launch", [])]
+            if vals:
+                roofline["traffic"] = float(np.mean(vals))
+                roofline["traffic_source"] = "mean over the captured launches of " + " / ".join(pick) + ", profiles/r2_traffic.json"
+            if cross and args.config in (2, 4):
+                cv = tj.get("config2", {}).get("k_cross_tc<64, 4, 0>", {}).get("dram_bytes_per_launch", [])
+                if cv:
+                    cross["traffic"] = float(np.mean(cv))
+    except Exception:
+        pass
     roofline["share_of_step"] = share
     if cross:
         roofline["cross"] = cross
