@@ -58,6 +58,7 @@ struct CrossParams {
     int64_t kblocks;       // ceil(len / BK)
     int64_t units;         // tiles * kblocks
     int k;                 // true rank
+    int slots;             // slots of Qp (most CTAs that touch one tile)
     double* Qp;            // [slots][ncol][k]
     const double* unscale; // [NP]: 1 / (s_A * s_F[a])
     int drain;             // k-blocks accumulated in TMEM between two drains into the fp64 registers
@@ -256,6 +257,18 @@ k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ 
                     const int a = half * CPT + c;
                     if (a < p.k) out[a] = MODE == 0 ? fma(cj, p.fsum[a], acc[c] * p.unscale[a]) : acc[c] * p.unscale[a];
                 }
+                // the CTA that finishes a tile zero-fills the slots nobody writes (consumers sum all p.slots of them): no
+                // memset of the whole partial buffer per launch
+                if (seg_end == (tile + 1) * KBn) {
+                    for (int64_t sp = slot + 1; sp < p.slots; sp++) {
+                        double* z = p.Qp + (sp * p.ncol + j) * p.k;
+#pragma unroll
+                        for (int c = 0; c < CPT; c++) {
+                            const int a = half * CPT + c;
+                            if (a < p.k) z[a] = 0.0;
+                        }
+                    }
+                }
             }
         }
     }
@@ -266,6 +279,7 @@ k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ 
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
 }
+
 
 // ---------------------------------------------------------------------------------------------------- operand preparation
 // |x| maxima as fp64 bit patterns (non-negative doubles order like unsigned integers)
@@ -426,14 +440,13 @@ void launch_np(const CrossPlan& plan, const __half* a_hi, const __half* a_lo, co
     const CUtensorMap mF_hi = make_map(f_hi, plan.len, NP, plan.ld_f, NP);
     const CUtensorMap mF_lo = MODE != 1 ? make_map(f_lo, plan.len, NP, plan.ld_f, NP) : mF_hi;
     CrossParams p;
-    p.ncol = plan.ncol; p.kblocks = plan.kblocks; p.units = plan.units; p.k = plan.k; p.Qp = Qp; p.unscale = unscale;
+    p.ncol = plan.ncol; p.kblocks = plan.kblocks; p.units = plan.units; p.k = plan.k; p.slots = plan.slots; p.Qp = Qp; p.unscale = unscale;
     static const int drain_env = [] { const char* e = getenv("NNLM_TC_DRAIN"); return e ? atoi(e) : 0; }();
     p.drain = drain > 0 ? drain : (drain_env > 0 ? drain_env : (NP >= 128 ? DRAIN_LARGE : DRAIN_SMALL));
     // the hi*lo + lo*hi accumulator is 2^-11 of the hi*hi one: its fp32 truncation matters 2^-11 as much, so it keeps
     // round 1's 1024 indices per drain and the epilogue converts half as many values on the other drains
     p.d1_every = MODE == 0 ? std::max(1, 16 / p.drain) : 1;
     p.center = center; p.fsum = fsum;
-    NNLM_CUDA_CHECK(cudaMemsetAsync(Qp, 0, sizeof(double) * (size_t)plan.slots * plan.ncol * plan.k, st));
     kern<<<plan.grid, THREADS, smem, st>>>(mA_hi, mA_lo, mF_hi, mF_lo, p);
     NNLM_LAUNCHED();
 }
