@@ -281,6 +281,211 @@ k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ 
 }
 
 
+
+// ---------------------------------------------------------------------------------------------------- pair contraction
+// k_mask_tc2: the exact integer contraction of the NA path (MODE 2's arithmetic) by a PAIR of CTAs (tcgen05 cta_group::2).
+// Why: k_cross_tc<128,4,2> moves 48 KB through L2 per k-block for 4.2 Mflop (87 flop/B) and sits on the chip's L2 -> SM ingest
+// cap (6200 of ~6300 B/clk: profiles/r2_d_config4.md). A pair forms D[256 x 256] = M[256 x K] * Z[256 x K]^T per k-step: CTA r
+// holds mask columns tile*256 + r*128 .. +128 (its half of the M operand and of the accumulator rows) and loads slice tile r
+// (its half of the N operand: N = slice 0 | slice 1); the tensor cores of both SMs read both halves of N. Per CTA and k-block
+// 32 KB for 4.2 Mflop (131 flop/B); TMEM per CTA 256 columns x 2 buffers; epilogue and fp64 register accumulators exactly as
+// MODE 2. The leader CTA (rank 0) issues the MMAs and owns the `full` barriers (both CTAs' TMA loads complete on them);
+// `empty` / `tfull` exist in both CTAs and are signalled by multicast commits; the peer's epilogue arrives remotely on the
+// leader's `tempty`.
+constexpr int P2_STAGES = 6;
+
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load of a pair: the bytes complete on the barrier at cluster address `bar_cluster` (the leader's)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {       // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+k_mask_tc2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapF0,
+           const __grid_constant__ CUtensorMap mapF1, const CrossParams p)
+{
+    constexpr int NP = 128;                                // Z columns per slice tile
+    constexpr int T_BYTES = 128 * BK * 2;                  // 16 KB: one 128-row operand tile per stage
+    constexpr int STAGE_BYTES = 2 * T_BYTES;               // this CTA's half of M and its half of N
+    constexpr int CPT = NP / 2;
+    // f16 x f16 -> f32, K-major, N = 256, M = 256
+    constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* tiles = smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + P2_STAGES * STAGE_BYTES);
+    uint64_t* empty = full + P2_STAGES;
+    uint64_t* tfull = empty + P2_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const int64_t P = gridDim.x / 2, pair = blockIdx.x / 2, U = p.units, KBn = p.kblocks;
+    const int64_t u0 = (pair * U) / P, u1 = ((pair + 1) * U) / P;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P2_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 2 * EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================================== TMA producer (both CTAs) =====================================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const CUtensorMap* mapF = rank == 0 ? &mapF0 : &mapF1;
+            for (int64_t u = u0; u < u1; u++) {
+                const int64_t tile = u / KBn, kb = u % KBn;
+                mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* sa = tiles + stage * STAGE_BYTES;
+                const uint32_t bar0 = mapa_rank(smem_u32(&full[stage]), 0);
+                if (rank == 0) mbar_expect_tx(&full[stage], 2 * STAGE_BYTES);      // both CTAs' bytes land on the leader's barrier
+                const int c0 = (int)(kb * BK), c1 = (int)(tile * 256 + rank * 128);
+                tma_load_2d_pair(sa, &mapA, bar0, c0, c1);                         // (rows past the end read as zero)
+                tma_load_2d_pair(sa + T_BYTES, mapF, bar0, c0, 0);
+                if (++stage == P2_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer (leader CTA only) =====================================
+        if (lane == 0 && rank == 0) {
+            int stage = 0; uint32_t phase = 0;
+            uint32_t chunk = 0;
+            int64_t u = u0;
+            while (u < u1) {
+                const int64_t tile = u / KBn;
+                const int64_t seg_end = min(u1, (tile + 1) * KBn);
+                while (u < seg_end) {
+                    const int64_t chunk_end = min(seg_end, u + (int64_t)p.drain);
+                    const uint32_t buf = chunk & 1, tph = (chunk >> 1) & 1;
+                    mbar_wait(&tempty[buf], tph ^ 1);           // both epilogues have drained this TMEM buffer
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + buf * 256;
+                    bool first = true;
+                    for (; u < chunk_end; u++) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(tiles + stage * STAGE_BYTES);
+                        const uint64_t a = make_desc(sa), f = make_desc(sa + T_BYTES);
+#pragma unroll
+                        for (int ks = 0; ks < BK / 16; ks++) {
+                            const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+                            umma_f16_pair(d, a + adv, f + adv, IDESC, (first && ks == 0) ? 0u : 1u);
+                        }
+                        first = false;
+                        tc_commit_pair(&empty[stage]);          // frees the stage in both CTAs when these MMAs retire
+                        if (++stage == P2_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    tc_commit_pair(&tfull[buf]);                // accumulators of this chunk are complete (both CTAs)
+                    chunk++;
+                }
+            }
+        }
+    } else {
+        // ===================================== epilogue (both CTAs): TMEM -> fp64 registers -> partial tile =====================================
+        const int ew = warp - 2;
+        const int quarter = warp & 3;
+        const int half = ew >> 2;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        uint32_t chunk = 0;
+        int64_t u = u0;
+        while (u < u1) {
+            const int64_t tile = u / KBn;
+            const int64_t seg_end = min(u1, (tile + 1) * KBn);
+            double acc[CPT];
+#pragma unroll
+            for (int c = 0; c < CPT; c++) acc[c] = 0.0;
+            while (u < seg_end) {
+                const int64_t chunk_end = min(seg_end, u + (int64_t)p.drain);
+                const uint32_t buf = chunk & 1, tph = (chunk >> 1) & 1;
+                mbar_wait(&tfull[buf], tph);
+                tc_fence_after();
+                const uint32_t t0 = tmem_base + lane_addr + buf * 256 + half * CPT;        // slice 0 sums
+                const uint32_t t1 = t0 + NP;                                               // slice 1 sums
+#pragma unroll
+                for (int ch = 0; ch < CPT / 32; ch++) {
+                    uint32_t r[32];
+                    TmemLd<32>::ld(t0 + ch * 32, r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int c = 0; c < 32; c++) acc[ch * 32 + c] += (double)__uint_as_float(r[c]);
+                }
+#pragma unroll
+                for (int ch = 0; ch < CPT / 32; ch++) {
+                    uint32_t r[32];
+                    TmemLd<32>::ld(t1 + ch * 32, r);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int c = 0; c < 32; c++) acc[ch * 32 + c] = fma((double)__uint_as_float(r[c]), LO_UNSCALE, acc[ch * 32 + c]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty[buf]), 0));   // on the leader's barrier
+                u = chunk_end;
+                chunk++;
+            }
+            const int64_t slot = pair - first_cta_of_unit(tile * KBn, U, P);
+            const int64_t j = tile * 256 + (int64_t)rank * 128 + row;
+            if (j < p.ncol) {
+                double* out = p.Qp + (slot * p.ncol + j) * p.k;
+#pragma unroll
+                for (int c = 0; c < CPT; c++) out[half * CPT + c] = acc[c] * p.unscale[half * CPT + c];
+                if (seg_end == (tile + 1) * KBn) {            // the pair that finishes a tile zero-fills the slots nobody writes
+                    for (int64_t sp = slot + 1; sp < p.slots; sp++) {
+                        double* z = p.Qp + (sp * p.ncol + j) * p.k;
+#pragma unroll
+                        for (int c = 0; c < CPT; c++) z[half * CPT + c] = 0.0;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                                       // nobody leaves while the partner may still read its shared memory
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------- operand preparation
 // |x| maxima as fp64 bit patterns (non-negative doubles order like unsigned integers)
 __global__ void k_rowmax(const double* __restrict__ F, int k, int64_t len, unsigned long long* __restrict__ rowmax)
@@ -457,17 +662,19 @@ bool cross_tc_supported(int k) { return k >= 1 && k <= 128; }
 int cross_tc_np(int k) { return k <= 32 ? 32 : (k <= 64 ? 64 : 128); }
 int64_t cross_tc_ld(int64_t len) { return (len + 7) / 8 * 8; }     // TMA row pitch must be a multiple of 16 bytes
 
-CrossPlan cross_tc_plan(int k, int64_t len, int64_t ncol)
+CrossPlan cross_tc_plan(int k, int64_t len, int64_t ncol, bool pairs)
 {
+    NNLM_REQUIRE(!pairs || k == 128, "the CTA-pair contraction runs on 128-row factor tiles");
     CrossPlan pl;
-    pl.k = k; pl.len = len; pl.ncol = ncol;
+    pl.k = k; pl.len = len; pl.ncol = ncol; pl.pairs = pairs;
     pl.np = cross_tc_np(k);
     pl.ld_a = cross_tc_ld(len);
     pl.ld_f = cross_tc_ld(len);
-    pl.tiles = ceil_div(ncol, BM);
+    pl.tiles = ceil_div(ncol, pairs ? 2 * BM : BM);
     pl.kblocks = ceil_div(len, BK);
     pl.units = pl.tiles * pl.kblocks;
-    pl.grid = (int)std::min<int64_t>(sm_count(), pl.units);
+    // pairs: `grid` counts PAIRS of CTAs (the launch uses 2 * grid CTAs in clusters of two)
+    pl.grid = (int)std::min<int64_t>(pairs ? sm_count() / 2 : sm_count(), pl.units);
     // most CTAs that touch one tile
     int64_t worst = 1;
     for (int64_t t = 0; t < pl.tiles; t++) {
@@ -504,6 +711,23 @@ void launch_cross_tc_exact2(const CrossPlan& plan, const __half* a_plane, const 
 {
     NNLM_REQUIRE(plan.np == 128, "the exact integer contraction runs on 128-row factor tiles");
     launch_np<128, 4, 2>(plan, a_plane, nullptr, f0, f1, unscale, nullptr, nullptr, Qp, 64, st);
+}
+
+// The same contraction by CTA pairs (k_mask_tc2); plan from cross_tc_plan(128, len, ncol, /*pairs=*/true).
+void launch_mask_tc2(const CrossPlan& plan, const __half* a_plane, const __half* f0, const __half* f1, const double* unscale,
+                     double* Qp, cudaStream_t st)
+{
+    NNLM_REQUIRE(plan.np == 128 && plan.pairs && plan.k == 128, "the CTA-pair contraction needs a pair plan of rank 128");
+    constexpr size_t smem = (size_t)P2_STAGES * 2 * 128 * BK * 2 + 1024 /*alignment slack*/ + 256;
+    NNLM_CUDA_CHECK(cudaFuncSetAttribute(k_mask_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const CUtensorMap mA = make_map(a_plane, plan.len, plan.ncol, plan.ld_a, 128);
+    const CUtensorMap mF0 = make_map(f0, plan.len, 128, plan.ld_f, 128);
+    const CUtensorMap mF1 = make_map(f1, plan.len, 128, plan.ld_f, 128);
+    CrossParams p;
+    p.ncol = plan.ncol; p.kblocks = plan.kblocks; p.units = plan.units; p.k = plan.k; p.slots = plan.slots; p.Qp = Qp; p.unscale = unscale;
+    p.drain = 64; p.d1_every = 1; p.center = nullptr; p.fsum = nullptr;
+    k_mask_tc2<<<2 * plan.grid, THREADS, smem, st>>>(mA, mF0, mF1, p);
+    NNLM_LAUNCHED();
 }
 
 void launch_means(const double* A, int64_t len, int64_t ncol, double* colmean, double* rowmean, cudaStream_t st)

@@ -261,18 +261,21 @@ void Engine::ingest_shards(const double* dAcol, const double* dArow)
             // the missing indicator as fp16 0/1 planes, and the scratch of the mask contraction
             const int64_t pt = na_packed_width(k_);
             size_t q2 = 0, sN = 0;
+            // the mask contraction runs on CTA pairs (k_mask_tc2: 131 flop per byte through L2 instead of 87);
+            // NNLM_NA_PAIRS=0 selects the single-CTA kernel (experiments)
+            static const bool na_pairs = [] { const char* e = std::getenv("NNLM_NA_PAIRS"); return !(e && atoi(e) == 0); }();
             if (mc_ > 0) {
                 mk_.alloc((size_t)ld_n * mc_);
                 NNLM_CUDA_CHECK(cudaMemsetAsync(mk_.p, 0, mk_.bytes(), st_));
                 launch_mask_planes<double>(dAcol, n_, mc_, mk_.p, ld_n, nullptr, 0, st_);
-                plan_na_h_ = cross_tc_plan(NA_TILE, n_, mc_);
+                plan_na_h_ = cross_tc_plan(NA_TILE, n_, mc_, na_pairs);
                 q2 = (size_t)plan_na_h_.slots * mc_ * NA_TILE; sN = (size_t)mc_ * pt;
             }
             if (both_sides_ && nr_ > 0) {
                 mkt_.alloc((size_t)ld_m * nr_);
                 NNLM_CUDA_CHECK(cudaMemsetAsync(mkt_.p, 0, mkt_.bytes(), st_));
                 launch_mask_planes<double>(dArow, nr_, m_, nullptr, 0, mkt_.p, ld_m, st_);
-                plan_na_w_ = cross_tc_plan(NA_TILE, m_, nr_);
+                plan_na_w_ = cross_tc_plan(NA_TILE, m_, nr_, na_pairs);
                 q2 = std::max(q2, (size_t)plan_na_w_.slots * nr_ * NA_TILE); sN = std::max(sN, (size_t)nr_ * pt);
             }
             zplanes_.alloc((size_t)NA_SLICES * NA_TILE * ld_f);

@@ -64,12 +64,13 @@ void launch_cross_simt(const double* Y, const TA* A, int k, int64_t len, int64_t
 // ---- cross_tc.cu: K2 on tcgen05 (fp16 hi/lo planes, fp32 TMEM accumulate drained into fp64, stream-K) ----
 struct CrossPlan {
     int k = 0, np = 0, grid = 0, slots = 0;
+    bool pairs = false;     // tiles of 256 columns worked by CTA pairs (grid counts pairs)
     int64_t len = 0, ncol = 0, ld_a = 0, ld_f = 0, tiles = 0, kblocks = 0, units = 0;
 };
 bool      cross_tc_supported(int k);
 int       cross_tc_np(int k);                 // padded rank (rows of the factor planes)
 int64_t   cross_tc_ld(int64_t len);           // row pitch (elements) of a plane whose rows hold `len` contraction indices
-CrossPlan cross_tc_plan(int k, int64_t len, int64_t ncol);
+CrossPlan cross_tc_plan(int k, int64_t len, int64_t ncol, bool pairs = false);
 // Qp[slot][ncol][k] (slots = plan.slots, zero-filled here) = partial cross-products; sum over slots = F * A.
 // a_* : planes of the A copy of this half (row j = column j of the matrix, pitch plan.ld_a); f_* : planes of the factor.
 // center[ncol] = the per-column mean that was subtracted from A before the split, fsum[k] = rowSums(F): the mean component
@@ -100,6 +101,9 @@ void launch_cross_tc_exact(const CrossPlan& plan, const __half* a_plane, const _
                            cudaStream_t st);
 void launch_cross_tc_exact2(const CrossPlan& plan, const __half* a_plane, const __half* f0, const __half* f1, const double* unscale,
                             double* Qp, cudaStream_t st);
+// the same by pairs of CTAs (tcgen05 cta_group::2) on 256-column tiles: plan from cross_tc_plan(128, len, ncol, true)
+void launch_mask_tc2(const CrossPlan& plan, const __half* a_plane, const __half* f0, const __half* f1, const double* unscale,
+                     double* Qp, cudaStream_t st);
 
 // ---- solve_ls.cu: K3/K4/K5 — warp-per-column sequential coordinate descent / Lee multiplicative, square loss ----
 // X (k x ncol) in/out; G regularised Gram (k x k); Qp split-K partials of Wt*A (splits x k x ncol); mask k x ncol bytes or null;

@@ -169,8 +169,11 @@ void launch_na_gram_tc(const CrossPlan& plan, const double* Y, int k, const __ha
         k_z_slices<<<(unsigned)ceil_div(ld, 64), 256, smem, st>>>(Y, k, len, ld, rowmax, p0, npairs, zplanes, zunscale);
         NNLM_LAUNCHED();
         for (int s = 0; s < ZS; s += 2) {              // two slices per pass over the mask plane
-            launch_cross_tc_exact2(plan, mask_plane, zplanes + (size_t)s * ZT * ld, zplanes + (size_t)(s + 1) * ZT * ld,
-                                   zunscale + s * ZT, Qp, st);
+            if (plan.pairs)
+                launch_mask_tc2(plan, mask_plane, zplanes + (size_t)s * ZT * ld, zplanes + (size_t)(s + 1) * ZT * ld, zunscale + s * ZT, Qp, st);
+            else
+                launch_cross_tc_exact2(plan, mask_plane, zplanes + (size_t)s * ZT * ld, zplanes + (size_t)(s + 1) * ZT * ld,
+                                       zunscale + s * ZT, Qp, st);
             k_fold<<<(int)std::min<int64_t>(ceil_div(ncol * ZT, 256), 148 * 16), 256, 0, st>>>(Qp, plan.slots, ncol, pt, p0, S);
             NNLM_LAUNCHED();
         }

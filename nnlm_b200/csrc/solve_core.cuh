@@ -20,7 +20,10 @@ namespace nnlm {
 
 // h: in/out column (rows lane+32*s); q: Wt*A.col(j) (same distribution); mk[s]: ballot of masked rows 32*s..32*s+31;
 // gs: shared Gram, gs[r + KR*c] = V[r,c], rows >= k zero. Returns the number of sweeps performed.
-template <int RPL, int METHOD>
+// TRI: gs holds only the lower triangle of the (symmetric) Gram, V[r,c] at r(r+1)/2 + c for r >= c — half the shared memory per
+// column, so the NA path keeps 16 instead of 10 columns in flight per SM at k = 50 (its solver is latency-bound); the
+// price is an address select per load and a strided (conflicting) access for the rows below the diagonal.
+template <int RPL, int METHOD, bool TRI = false>
 __device__ __forceinline__ unsigned warp_solve_ls(double (&h)[RPL], const double (&q)[RPL], const unsigned (&mk)[RPL],
                                                   const double* gs, int k, double l1, unsigned max_iter, double rel_tol,
                                                   int ldg = 32 * RPL)
@@ -30,6 +33,13 @@ __device__ __forceinline__ unsigned warp_solve_ls(double (&h)[RPL], const double
     // column into a mu that is never consumed (their h is 0, their 1/V_rr is 0 and they never own a coordinate).
     const int KR = ldg;
     const int lane = threadIdx.x & 31;
+    int rr[RPL], tb[RPL];                               // TRI: this lane's rows (clamped into the matrix) and their triangle offsets
+#pragma unroll
+    for (int s = 0; s < RPL; s++) { rr[s] = min(lane + 32 * s, k - 1); tb[s] = rr[s] * (rr[s] + 1) / 2; }
+    auto gi = [&](int s, int c) -> int {                // index of V[row s of this lane, c]
+        if (!TRI) return lane + 32 * s + KR * c;
+        return rr[s] >= c ? tb[s] + c : c * (c + 1) / 2 + rr[s];
+    };
     unsigned t = 0;
     bool cont = true;                                   // rel_err starts at 1 + rel_tol
     if (METHOD == 1) {
@@ -44,7 +54,7 @@ __device__ __forceinline__ unsigned warp_solve_ls(double (&h)[RPL], const double
                 if (c >= k) break;
                 const double hc = shfl_d(h[sc], lc);
 #pragma unroll
-                for (int s = 0; s < RPL; s++) mu[s] = fma(gs[lane + 32 * s + KR * c], hc, mu[s]);
+                for (int s = 0; s < RPL; s++) mu[s] = fma(gs[gi(s, c)], hc, mu[s]);
             }
         }
 #pragma unroll
@@ -59,7 +69,7 @@ __device__ __forceinline__ unsigned warp_solve_ls(double (&h)[RPL], const double
 #pragma unroll
         for (int s = 0; s < RPL; s++) {
             const int r = lane + 32 * s;
-            rinv[s] = (r < k) ? 1.0 / gs[r + KR * r] : 0.0;
+            rinv[s] = (r < k) ? 1.0 / gs[TRI ? tb[s] + r : r + KR * r] : 0.0;
         }
         bool anymask = false;
 #pragma unroll
@@ -75,7 +85,7 @@ __device__ __forceinline__ unsigned warp_solve_ls(double (&h)[RPL], const double
                     const int cnt = min(32, k - 32 * sc);
                     double gn[RPL];
 #pragma unroll
-                    for (int s = 0; s < RPL; s++) gn[s] = gs[lane + 32 * s + KR * min(32 * sc, k - 1)];
+                    for (int s = 0; s < RPL; s++) gn[s] = gs[gi(s, min(32 * sc, k - 1))];
                     for (int lc = 0; lc < cnt; lc++) {
                         const int c = 32 * sc + lc;
                         double g[RPL];
@@ -83,7 +93,7 @@ __device__ __forceinline__ unsigned warp_solve_ls(double (&h)[RPL], const double
                         for (int s = 0; s < RPL; s++) g[s] = gn[s];
                         const int cn = (lc + 1 < cnt) ? c + 1 : c;
 #pragma unroll
-                        for (int s = 0; s < RPL; s++) gn[s] = gs[lane + 32 * s + KR * cn];
+                        for (int s = 0; s < RPL; s++) gn[s] = gs[gi(s, cn)];
                         const double hc = h[sc];
                         double cand = fma(-mu[sc], rinv[sc], hc);
                         const int keep = ~(__double2hiint(cand) >> 31);                       // max(cand, +0) on the bit pattern
@@ -118,7 +128,7 @@ __device__ __forceinline__ unsigned warp_solve_ls(double (&h)[RPL], const double
                     const double down = cand - hc;
                     const double d = shfl_d(down, lc);
 #pragma unroll
-                    for (int s = 0; s < RPL; s++) mu[s] = fma(d, gs[lane + 32 * s + KR * c], mu[s]);
+                    for (int s = 0; s < RPL; s++) mu[s] = fma(d, gs[gi(s, c)], mu[s]);
                     if (lane == lc) {
                         h[sc] = cand;
                         flag = flag || (2 * fabs(down) > rel_tol * (cand + hc + TINY_NUM));
@@ -138,7 +148,7 @@ __device__ __forceinline__ unsigned warp_solve_ls(double (&h)[RPL], const double
                     if ((mk[sc] >> lc) & 1u) continue;
                     double part = 0.0;
 #pragma unroll
-                    for (int s = 0; s < RPL; s++) part = fma(gs[lane + 32 * s + KR * c], h[s], part);
+                    for (int s = 0; s < RPL; s++) part = fma(gs[gi(s, c)], h[s], part);
                     const double den = warp_sum(part) + l1;
                     const double ratio = shfl_d(q[sc], lc) / (den + TINY_NUM);
                     if (lane == lc) h[sc] *= ratio;

@@ -18,6 +18,7 @@
 // "Missing" is bit-exactly the reference's predicate: the entry is not finite (find_finite, :80-83), evaluated on the
 // stored value of A (fp64, or fp32 whose non-finite set is identical by construction of the conversion).
 #include <algorithm>
+#include <string>
 #include <cstdlib>
 
 #include "kernels.cuh"
@@ -226,7 +227,7 @@ k_solve_batch(double* __restrict__ X, const double* __restrict__ Gin, const doub
 
 // Kernel B': as kernel B, with the per-column Gram assembled on the fly from the shared raw Gram and the packed tensor-core
 // corrections of na_gram.cu: G_j[a,b] = Gfull[a,b] - S[j][pair(max, min)] + regularisation (src/update_with_missing.cpp:98-103).
-template <int RPL, int METHOD>
+template <int RPL, int METHOD, bool TRI>
 __global__ void __launch_bounds__(512)
 k_solve_batch_packed(double* __restrict__ X, const double* __restrict__ Gfull, const double* __restrict__ S, int64_t pt,
                      const double* __restrict__ Qp, int splits, const double* __restrict__ center, const uint8_t* __restrict__ mask,
@@ -235,10 +236,11 @@ k_solve_batch_packed(double* __restrict__ X, const double* __restrict__ Gfull, c
 {
     extern __shared__ __align__(32) double smd[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-    const int per_warp = k * k + 32 * RPL;           // columns packed at pitch k + slack for the lanes beyond row k (solve_core.cuh)
+    const int kk2 = k * (k + 1) / 2;
+    // TRI: the lower triangle only (solve_core.cuh); else columns packed at pitch k + slack for the lanes beyond row k
+    const int per_warp = TRI ? kk2 : k * k + 32 * RPL;
     double* gs = smd + (size_t)warp * per_warp;
     unsigned long long my_sweeps = 0;
-    const int kk2 = k * (k + 1) / 2;
     for (int e = lane; e < per_warp; e += 32) gs[e] = 0.0;
     for (int64_t col = (int64_t)blockIdx.x * wpc + warp; col < ncol; col += (int64_t)gridDim.x * wpc) {
         const uint8_t* mcol = mask ? mask + (int64_t)k * col : nullptr;
@@ -259,8 +261,8 @@ k_solve_batch_packed(double* __restrict__ X, const double* __restrict__ Gfull, c
             if (p0 != p1 && a == b) g += p0 - p1;
             if (p1 != 0.0) g += p1;
             if (a == b) g += TINY_NUM;
-            gs[a + k * b] = g;
-            gs[b + k * a] = g;
+            if (TRI) gs[p] = g;
+            else { gs[a + k * b] = g; gs[b + k * a] = g; }
         }
         __syncwarp();
         double h[RPL], q[RPL];
@@ -280,7 +282,7 @@ k_solve_batch_packed(double* __restrict__ X, const double* __restrict__ Gfull, c
             const bool mb = valid && mcol != nullptr && mcol[r] != 0;
             mk[s] = __ballot_sync(0xffffffffu, mb);
         }
-        my_sweeps += warp_solve_ls<RPL, METHOD>(h, q, mk, gs, k, l1, max_iter, rel_tol, k);
+        my_sweeps += warp_solve_ls<RPL, METHOD, TRI>(h, q, mk, gs, k, l1, max_iter, rel_tol, k);
 #pragma unroll
         for (int s = 0; s < RPL; s++) {
             const int r = lane + 32 * s;
@@ -295,10 +297,14 @@ void launch_packed_rpl(int method, double* X, const double* Gfull, const double*
                        const double* center, const uint8_t* mask, int k, int64_t ncol, const double* pen, unsigned max_iter,
                        double rel_tol, unsigned long long* sweeps, cudaStream_t st)
 {
-    const size_t per_warp = sizeof(double) * ((size_t)k * k + 32 * RPL);
+    // the per-column Gram is kept as its lower triangle (16 instead of 10 columns in flight per SM at k = 50);
+    // NNLM_NA_SOLVER=square selects the full square at pitch k (experiments)
+    static const bool square = [] { const char* e = getenv("NNLM_NA_SOLVER"); return e && std::string(e) == "square"; }();
+    const size_t per_warp = sizeof(double) * (square ? (size_t)k * k + 32 * RPL : (size_t)k * (k + 1) / 2);
     const int wpc = std::max(1, std::min(16, (int)(220 * 1024 / per_warp)));      // columns in flight per SM
     const size_t smem = (size_t)wpc * per_warp;
-    auto kb = method == 1 ? k_solve_batch_packed<RPL, 1> : k_solve_batch_packed<RPL, 2>;
+    auto kb = square ? (method == 1 ? k_solve_batch_packed<RPL, 1, false> : k_solve_batch_packed<RPL, 2, false>)
+                     : (method == 1 ? k_solve_batch_packed<RPL, 1, true> : k_solve_batch_packed<RPL, 2, true>);
     NNLM_CUDA_CHECK(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(ncol, wpc), 148));
     kb<<<grid, 32 * wpc, smem, st>>>(X, Gfull, S, pt, Qp, splits, center, mask, k, ncol, pen[0], pen[1], pen[2], max_iter, rel_tol, sweeps);
