@@ -359,10 +359,10 @@ def main():
         launches_per_half = -(-P // 128) * 2          # 128 Z columns x 2 slices per pass over the mask plane
         mask_bytes = 2.0 * launches_per_half * n * m * 2 / world
         roofline = {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None,
-                    "kernel": "k_cross_tc<128,4,2> x %d launches per half (mask x Khatri-Rao slices, two slices per pass) + k_z_slices + k_fold, per GPU" % launches_per_half,
+                    "kernel": "k_mask_tc2 (tcgen05 cta_group::2) x %d launches per half (mask x Khatri-Rao slices, two slices per pass) + k_z_slices + k_fold, per GPU" % launches_per_half,
                     "algorithmic_flop_per_step": flops, "ms_per_step_in_these_kernels": t * 1e3, "peak_source": tsrc,
                     "hbm_side": {"achieved": mask_bytes / t / 1e9 if t > 0 else 0.0, "peak": hbm_peak, "unit": "GB/s",
-                                 "bytes_per_step": mask_bytes, "what": "fp16 mask plane streamed once per launch (the two slice planes of Z come from L2: 2x these bytes)"},
+                                 "bytes_per_step": mask_bytes, "what": "fp16 mask plane streamed once per launch (the slice planes of Z come from L2: as many bytes again on CTA pairs)"},
                     "solve_ms_per_step": st["solve_ms"] / args.steps}
     # DRAM traffic per launch of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum from the `ncu --set full`
     # captures summarised in profiles/r2_traffic.json (a citation of those captures, valid for the full-size single-GPU
@@ -371,7 +371,7 @@ def main():
         tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
         if world == 1 and not args.small and not args.shape:
             pick = {2: ["k_scd_chain<13, 2>", "k_scd_chain<13, 1>"], 5: [], 3: ["k_solve_kl_fast<4, 10>", "k_solve_kl_fast<4, 13>"],
-                    4: ["k_cross_tc<128, 4, 2>"]}[args.config]
+                    4: ["k_mask_tc2"]}[args.config]
             vals = [v for kname in pick for v in tj.get(f"config{args.config}", {}).get(kname, {}).get("dram_bytes_per_launch", [])]
             if vals:
                 roofline["traffic"] = float(np.mean(vals))
