@@ -197,11 +197,17 @@ k_solve_kl_fast(double* __restrict__ X, const float* __restrict__ Y32, const flo
     for (int c = tid; c < k; c += KLF_NT) sw[c] = sumY[c];
 #pragma unroll
     for (int e = 0; e < 2 * E; e++) yS[(size_t)e * KLF_NT + tid] = 0.0f;       // a never-staged buffer must not hold NaN (k == 1)
+#ifdef NNLM_KLF_PROF
+    long long pk_wait = 0, pk_pass = 0, pk_red = 0, pk_send = 0, pk_xch = 0, pk_upd = 0, pk_n = 0, pk_ga = 0, pk_gi = 0, pk_g = 0;
+#endif
     unsigned step = 0;      // coordinate steps since kernel start: parity of the cluster exchange buffers (never reset, so a CTA
                             // that runs ahead into the next column group cannot overwrite a record a peer still reads)
 
     for (int64_t grp = cid; grp * KLF_J < ncol; grp += nclusters) {
         const int64_t col0 = grp * KLF_J;
+#ifdef NNLM_KLF_PROF
+        long long pg0 = clock64();
+#endif
         __syncthreads();
         for (int e2 = tid; e2 < KLF_J * k; e2 += KLF_NT) {
             const int j = e2 / k, c = e2 % k;
@@ -220,7 +226,7 @@ k_solve_kl_fast(double* __restrict__ X, const float* __restrict__ Y32, const flo
 
         // per-column control state lives in lane j of warp 0 of every CTA (identical across the cluster by construction)
         bool active = false, cont = false, flag = false;
-        double sumH = 0.0;
+        double sumH = 0.0, rden = 0.0;
         unsigned tcount = 0;
         if (warp == 0 && lane < KLF_J) {
             const int j = lane;
@@ -233,27 +239,56 @@ k_solve_kl_fast(double* __restrict__ X, const float* __restrict__ Y32, const flo
             cont = active;
         }
 
-        // wh = Yr' h (base_algorithms.cpp:82,133), fp32; rows staged two ahead
+#ifdef NNLM_KLF_PROF
+        long long pg1 = clock64(); pk_ga += pg1 - pg0;
+#endif
+        // wh = Yr' h (base_algorithms.cpp:82,133), fp32
         float wh[E][KLF_J];
 #pragma unroll
         for (int e = 0; e < E; e++)
 #pragma unroll
             for (int j = 0; j < KLF_J; j++) wh[e][j] = 0.0f;
-        prefetch_row(0, 0);
-        for (int c = 0; c < k; c++) {
-            cp_async_wait_all();
-            if (c + 1 < k) prefetch_row(c + 1, (c + 1) & 1);
-            float hc[KLF_J];
+        // (rows straight from L2 into registers, two to four rows = up to 26 loads in flight per thread: staged one row ahead through shared
+        // memory like the sweeps below, every coordinate paid the full L2 latency — this loop was 60 % of the H-half at config 3)
+        {
+            constexpr int UB = E <= 6 ? 4 : (E <= 9 ? 3 : 2);          // rows in flight: as many as the register budget takes
+            int c = 0;
+            for (; c + UB <= k; c += UB) {
+                float y4[UB][E];
 #pragma unroll
-            for (int j = 0; j < KLF_J; j++) hc[j] = (float)hs[j * k + c];
+                for (int u = 0; u < UB; u++)
 #pragma unroll
-            for (int e = 0; e < E; e++) {
-                const float y = yS[((size_t)(c & 1) * E + e) * KLF_NT + tid];
+                    for (int e = 0; e < E; e++)
+                        y4[u][e] = ((valid >> e) & 1u) ? __ldg(y_gbase + (int64_t)(c + u) * len + (size_t)((uint32_t)e * stride_u)) : 0.0f;
 #pragma unroll
-                for (int j = 0; j < KLF_J; j++) wh[e][j] = fmaf(y, hc[j], wh[e][j]);
+                for (int u = 0; u < UB; u++) {
+                    float hc[KLF_J];
+#pragma unroll
+                    for (int j = 0; j < KLF_J; j++) hc[j] = (float)hs[j * k + c + u];
+#pragma unroll
+                    for (int e = 0; e < E; e++)
+#pragma unroll
+                        for (int j = 0; j < KLF_J; j++) wh[e][j] = fmaf(y4[u][e], hc[j], wh[e][j]);
+                }
+            }
+            for (; c < k; c++) {
+                float y1[E];
+#pragma unroll
+                for (int e = 0; e < E; e++)
+                    y1[e] = ((valid >> e) & 1u) ? __ldg(y_gbase + (int64_t)c * len + (size_t)((uint32_t)e * stride_u)) : 0.0f;
+                float hc[KLF_J];
+#pragma unroll
+                for (int j = 0; j < KLF_J; j++) hc[j] = (float)hs[j * k + c];
+#pragma unroll
+                for (int e = 0; e < E; e++)
+#pragma unroll
+                    for (int j = 0; j < KLF_J; j++) wh[e][j] = fmaf(y1[e], hc[j], wh[e][j]);
             }
         }
 
+#ifdef NNLM_KLF_PROF
+        pk_gi += clock64() - pg1; pk_g++;
+#endif
         float dprev[KLF_J];                       // pending rank-1 step of the previous coordinate (applied with its row)
 #pragma unroll
         for (int j = 0; j < KLF_J; j++) dprev[j] = 0.0f;
@@ -264,7 +299,13 @@ k_solve_kl_fast(double* __restrict__ X, const float* __restrict__ Y32, const flo
         for (unsigned t = 0; t < max_iter && more; t++) {
             for (int c = 0; c < k; c++) {
                 const int cur = ystep & 1;
+#ifdef NNLM_KLF_PROF
+                long long pk0 = clock64();
+#endif
                 cp_async_wait_all();
+#ifdef NNLM_KLF_PROF
+                long long pk1 = clock64(); pk_wait += pk1 - pk0;
+#endif
                 // ---- the pass of coordinate c over this thread's entries ----
                 float pa[KLF_J], pb[KLF_J];
 #pragma unroll
@@ -298,6 +339,9 @@ k_solve_kl_fast(double* __restrict__ X, const float* __restrict__ Y32, const flo
                     const int cn = (c + 1 < k) ? c + 1 : 0;
                     prefetch_row(cn, cur ^ 1);
                 }
+#ifdef NNLM_KLF_PROF
+                long long pk2 = clock64(); pk_pass += pk2 - pk1;
+#endif
                 // ---- fixed-order reduction: warp butterfly (fp32) -> warp totals -> CTA record -> cluster records (fp64) ----
                 constexpr int NVM = METHOD == 3 ? 2 * KLF_J : KLF_J;       // values reduced per coordinate: a (and b) per column
                 float vals[NVM];
@@ -312,6 +356,10 @@ k_solve_kl_fast(double* __restrict__ X, const float* __restrict__ Y32, const flo
                 // this CTA has finished reading step s, so a record is never overwritten while it is still needed.
                 const uint32_t buf = step & 1;
                 double* mine = xch + buf * KLF_MAXS * KLF_NV;
+#ifdef NNLM_KLF_PROF
+                long long pk3 = clock64(); pk_red += pk3 - pk2;
+                long long pk4 = pk3;
+#endif
                 if (warp == 0) {
                     double s = 0.0;
                     if (lane < NVM) {
@@ -327,9 +375,21 @@ k_solve_kl_fast(double* __restrict__ X, const float* __restrict__ Y32, const flo
                             const uint32_t slot = xch_s + 8u * (buf * KLF_MAXS * KLF_NV + rank * KLF_NV + lane);
                             for (int r = 0; r < S; r++) st_async_f64(map_to_rank(slot, r), s, map_to_rank(bar_s + 8 * buf, r));
                         }
-                        mbar_wait_cluster(bar_s + 8 * buf, (step >> 1) & 1);
+#ifdef NNLM_KLF_PROF
+                        pk4 = clock64(); pk_send += pk4 - pk3;
+#endif
                     }
+                    // while the records travel: the reciprocal of the multiplicative rule's denominator (:141-142) — it depends on
+                    // h and sum(h) only, and a fp64 division is ~30 dependent instructions that used to sit behind the wait
+                    if (METHOD == 4 && lane < KLF_J) {
+                        const double hc = hs[lane * k + c];
+                        rden = 1.0 / (sw[c] + b0 * hc + b1 * (sumH - hc) + b2);
+                    }
+                    if (S > 1) mbar_wait_cluster(bar_s + 8 * buf, (step >> 1) & 1);
                 }
+#ifdef NNLM_KLF_PROF
+                long long pk5 = clock64(); pk_xch += pk5 - pk4;
+#endif
                 // ---- the update of coordinate c: lane j of warp 0 owns column j (every CTA computes the same numbers) ----
                 if (warp == 0 && lane < KLF_J) {
                     const int j = lane;
@@ -348,16 +408,14 @@ k_solve_kl_fast(double* __restrict__ X, const float* __restrict__ Y32, const flo
                             if (cand < 0) cand = 0;
                             if (cand != hc) {
                                 d = cand - hc;
-                                const double er = 2 * fabs(hc - cand) / (cand + hc + tiny);
-                                flag = flag || (er > rel_tol);
+                                flag = flag || (2 * fabs(hc - cand) > rel_tol * (cand + hc + tiny));
                                 hn = cand;
                             }
                         } else {
-                            const double ratio = ta / (sw[c] + b0 * hc + b1 * (sumH - hc) + b2);   // :141-142
+                            const double ratio = ta * rden;                                   // :141-142 (reciprocal formed above)
                             d = (ratio - 1) * hc;
                             hn = hc * ratio;
-                            const double er = 2 * fabs(ratio - 1) / (ratio + 1);
-                            flag = flag || (er > rel_tol);
+                            flag = flag || (2 * fabs(ratio - 1) > rel_tol * (ratio + 1));     // 2|r-1|/(r+1) > tol, r + 1 > 0
                         }
                         sumH += d;
                         hs[j * k + c] = hn;
@@ -371,6 +429,9 @@ k_solve_kl_fast(double* __restrict__ X, const float* __restrict__ Y32, const flo
                     }
                 }
                 __syncthreads();
+#ifdef NNLM_KLF_PROF
+                pk_upd += clock64() - pk5; pk_n++;
+#endif
 #pragma unroll
                 for (int j = 0; j < KLF_J; j++) dprev[j] = dS[j];
                 step++;
@@ -395,6 +456,11 @@ k_solve_kl_fast(double* __restrict__ X, const float* __restrict__ Y32, const flo
             if (lane == 0 && tot) atomicAdd(sweeps, tot);
         }
     }
+#ifdef NNLM_KLF_PROF
+    if (tid == 0 && cid == 0 && pk_n > 0)
+        printf("klf prof S=%d E=%d rank=%d steps=%lld | per step: row wait %lld pass %lld reduce %lld send %lld exchange wait %lld update %lld cycles | per group (%lld): stage A+h %lld, wh init %lld\n",
+               S, E, rank, pk_n, pk_wait / pk_n, pk_pass / pk_n, pk_red / pk_n, pk_send / pk_n, pk_xch / pk_n, pk_upd / pk_n, pk_g, pk_ga / pk_g, pk_gi / pk_g);
+#endif
     if (S > 1) cluster.sync();      // no CTA exits while a peer may still write into its exchange buffer
 }
 
@@ -426,9 +492,8 @@ void launch_e(const KlfShape& sh, double* X, const float* Y32, const float* A, c
     const size_t smem = klf_smem(k, E);
     NNLM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t groups = ceil_div(ncol, KLF_J);
-    const int64_t clusters = std::max<int64_t>(1, std::min<int64_t>(groups, 148 / sh.S));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(clusters * sh.S));
+    cfg.gridDim = dim3((unsigned)(148 / sh.S * sh.S));
     cfg.blockDim = dim3(KLF_NT);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
@@ -436,6 +501,17 @@ void launch_e(const KlfShape& sh, double* X, const float* Y32, const float* A, c
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)sh.S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    // One cluster per slot that can be RESIDENT: a cluster must sit inside one GPC, so 148 / S overestimates (18 clusters of 8
+    // were launched where 15-16 fit; the rest ran as a second wave and doubled the H-half of config 3: profiles/r2_c_kl.md)
+    static int resident[KLF_MAXS + 1][17] = {};
+    int& res = resident[sh.S][E];
+    if (res == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148 / sh.S; }
+        res = n;
+    }
+    const int64_t clusters = std::max<int64_t>(1, std::min<int64_t>(groups, std::min<int64_t>(res, 148 / sh.S)));
+    cfg.gridDim = dim3((unsigned)(clusters * sh.S));
     NNLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, X, Y32, A, sumY, mask, k, len, ncol, pen[0], pen[1], pen[2], max_iter, rel_tol, sweeps));
     NNLM_LAUNCHED();
 }
