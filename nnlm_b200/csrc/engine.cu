@@ -427,10 +427,24 @@ void Engine::run_half_t(const Half& h)
         launch_rowsum(h.Y, k_, h.len, rowsum_part_.p, sumY_.p, st_);                       // :27
         if (fast_kl) launch_factor_rows_f32(h.Y, k_, h.len, Yr32_.p, st_);
         else launch_transpose_d(h.Y, k_, h.len, Yr_.p, st_);
+        // the solvers start every column from wh = Y' x: formed for all columns at once on the tensor cores (fp16 hi/lo planes
+        // of both factors, the scheme of the loss evaluation) instead of k passes over the factor rows per column group
+        const float* wh0 = nullptr;
+        if (fast_kl && error_tc_supported(k_) && h.ncol > 0 && std::getenv("NNLM_KL_NO_PRODUCT") == nullptr) {
+            const int kp = error_tc_kp(k_);
+            ew_hi_.ensure((size_t)h.len * kp); ew_lo_.ensure((size_t)h.len * kp); rsw_.ensure(4);
+            eh_hi_.ensure((size_t)h.ncol * kp); eh_lo_.ensure((size_t)h.ncol * kp); rsh_.ensure(4);
+            wh32_.ensure((size_t)h.len * h.ncol);
+            unsigned long long* mxb = reinterpret_cast<unsigned long long*>(small_.p + 10);
+            launch_split_rows(h.Y, k_, h.len, ew_hi_.p, ew_lo_.p, rsw_.p, mxb, st_);
+            launch_split_rows(h.X, k_, h.ncol, eh_hi_.p, eh_lo_.p, rsh_.p, mxb + 1, st_);
+            launch_product_tc(h.len, h.ncol, k_, ew_hi_.p, ew_lo_.p, rsw_.p, eh_hi_.p, eh_lo_.p, rsh_.p, wh32_.p, st_);
+            wh0 = wh32_.p;
+        }
         timer.end(st_);
         timer.begin(KernelTimer::SOLVE, st_);
         if (fast_kl)
-            launch_solve_kl_fast(method_, h.X, Yr32_.p, reinterpret_cast<const float*>(A), sumY_.p, h.mask, k_, h.len, h.ncol, h.pen,
+            launch_solve_kl_fast(method_, h.X, Yr32_.p, reinterpret_cast<const float*>(A), wh0, sumY_.p, h.mask, k_, h.len, h.ncol, h.pen,
                                  inner_max_iter_, inner_rel_tol_, sweeps_.p, st_);
         else
             launch_solve_kl<TA>(method_, h.X, Yr_.p, A, sumY_.p, h.mask, k_, h.len, h.ncol, h.pen, inner_max_iter_,

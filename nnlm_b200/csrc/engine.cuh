@@ -169,6 +169,7 @@ private:
     CrossPlan plan_h_, plan_w_;
     int precision_req_ = NNLM_PREC_AUTO;
     DevBuf<float> Yr32_;            // fp32 row-major copy of the fixed factor (KL fast path)
+    DevBuf<float> wh32_;            // len x ncol product of the factors a KL half starts from (KL fast path)
     DevBuf<double> Wt_, H_;         // whole factors, k x (chunk_n * R) and k x (chunk_m * R)
     DevBuf<uint8_t> Wm_, Hm_;       // k x n, k x m or empty
     bool has_wm_ = false, has_hm_ = false;

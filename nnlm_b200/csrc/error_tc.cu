@@ -42,6 +42,7 @@ struct ErrParams {
     const float* rsw;          // [1]  1 / s_W (one power-of-two scale per factor: the fp16 halves are floating-point, so
     const float* rsh;          // [1]  1 / s_H  every entry keeps its 22 bits down to 2^-27 of the largest one)
     double* part;              // [gridDim.x][2]
+    float* out;                // MODE 1: the product tile goes here, out[i + n * j] (same layout as A)
 };
 
 // g(x) = x - log1p(x) for |x| < 1/8 as x^2 (1/2 - x/3 + x^2/4 - ...): nine terms leave < 2e-9 relative
@@ -69,6 +70,9 @@ __device__ __noinline__ float kl_term_general(float a, float ah)
     return ae * (x - log1pf(x));
 }
 
+// MODE 0: the two losses. MODE 1: no loss, the tile of Ahat itself is written out in fp32 (the KL solvers start every column
+// from wh = W h: formed here at tensor-core speed instead of k passes over the factor rows per column group, solve_kl_fast.cuh).
+template <int MODE>
 __global__ void __launch_bounds__(E_THREADS, 1)
 k_error_tc(const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo,
            const __grid_constant__ CUtensorMap mapH_hi, const __grid_constant__ CUtensorMap mapH_lo, const ErrParams p)
@@ -166,6 +170,30 @@ k_error_tc(const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ 
             const int64_t j0 = (t / p.tiles_i) * TN + part * 32;
             const uint32_t buf = it & 1, tph = (it >> 1) & 1;
             const bool row_ok = i < p.n;
+            if (MODE == 1) {
+                mbar_wait(&tfull[buf], tph);
+                tc_fence_after();
+#pragma unroll
+                for (int ch = 0; ch < 2; ch++) {
+                    uint32_t r0[16], r1[16];
+                    const uint32_t t0 = tmem_base + lane_addr + buf * (2 * TN) + part * 32 + ch * 16;
+                    TmemLd<16>::ld(t0, r0);
+                    TmemLd<16>::ld(t0 + TN, r1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (ch == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[buf]);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 16; c++) {
+                        const int64_t j = j0 + ch * 16 + c;
+                        if (row_ok && j < p.m)
+                            p.out[i + p.n * j] = fmaf(__uint_as_float(r1[c]), (float)LO_UNSCALE, __uint_as_float(r0[c])) * unscale;
+                    }
+                }
+                continue;
+            }
             // this thread's 32 entries of A: every load is issued before the tile is waited for, so
             // their latency hides behind the MMA (a first version loaded inside the compute loop, behind its branches: 64
             // serialised L2 round trips per tile, 8 ms per evaluation instead of 0.5)
@@ -228,7 +256,7 @@ k_error_tc(const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (MODE == 0 && threadIdx.x == 0) {
         double a0 = 0.0, a1 = 0.0;
 #pragma unroll
         for (int w = 0; w < E_EPI_WARPS; w++) { a0 += red[2 * w]; a1 += red[2 * w + 1]; }
@@ -303,16 +331,34 @@ void launch_error_tc(const float* A, int64_t n, int64_t m, int k, const __half* 
     NNLM_REQUIRE(error_tc_supported(k), "tensor-core error evaluation supports rank k <= 128");
     const int kp = error_tc_kp(k);
     constexpr size_t smem = (size_t)E_STAGES * STAGE_BYTES + 1024 + 512;
-    NNLM_CUDA_CHECK(cudaFuncSetAttribute(k_error_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NNLM_CUDA_CHECK(cudaFuncSetAttribute(k_error_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ErrParams p;
     p.n = n; p.m = m; p.tiles_i = ceil_div(n, TM); p.tiles_j = ceil_div(m, TN); p.kblocks = kp / TK;
-    p.A = A; p.rsw = rsw; p.rsh = rsh; p.part = part;
+    p.A = A; p.rsw = rsw; p.rsh = rsh; p.part = part; p.out = nullptr;
     const CUtensorMap mW_hi = make_map(w_hi, kp, n, kp, TM), mW_lo = make_map(w_lo, kp, n, kp, TM);
     const CUtensorMap mH_hi = make_map(h_hi, kp, m, kp, TN), mH_lo = make_map(h_lo, kp, m, kp, TN);
     const int grid = error_tc_grid(n, m);
-    k_error_tc<<<grid, E_THREADS, smem, st>>>(mW_hi, mW_lo, mH_hi, mH_lo, p);
+    k_error_tc<0><<<grid, E_THREADS, smem, st>>>(mW_hi, mW_lo, mH_hi, mH_lo, p);
     NNLM_LAUNCHED();
     launch_reduce_partials(part, grid, 2, out, st);
+}
+
+// out[i + n * j] = sum_c W[c, i] H[c, j] in fp32 (~2^-22 relative): W planes [n][kp], H planes [m][kp] from launch_split_rows
+void launch_product_tc(int64_t n, int64_t m, int k, const __half* w_hi, const __half* w_lo, const float* rsw, const __half* h_hi,
+                       const __half* h_lo, const float* rsh, float* out, cudaStream_t st)
+{
+    NNLM_REQUIRE(error_tc_supported(k), "the tensor-core factor product supports rank k <= 128");
+    if (n <= 0 || m <= 0) return;
+    const int kp = error_tc_kp(k);
+    constexpr size_t smem = (size_t)E_STAGES * STAGE_BYTES + 1024 + 512;
+    NNLM_CUDA_CHECK(cudaFuncSetAttribute(k_error_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ErrParams p;
+    p.n = n; p.m = m; p.tiles_i = ceil_div(n, TM); p.tiles_j = ceil_div(m, TN); p.kblocks = kp / TK;
+    p.A = nullptr; p.rsw = rsw; p.rsh = rsh; p.part = nullptr; p.out = out;
+    const CUtensorMap mW_hi = make_map(w_hi, kp, n, kp, TM), mW_lo = make_map(w_lo, kp, n, kp, TM);
+    const CUtensorMap mH_hi = make_map(h_hi, kp, m, kp, TN), mH_lo = make_map(h_lo, kp, m, kp, TN);
+    k_error_tc<1><<<error_tc_grid(n, m), E_THREADS, smem, st>>>(mW_hi, mW_lo, mH_hi, mH_lo, p);
+    NNLM_LAUNCHED();
 }
 
 }  // namespace nnlm

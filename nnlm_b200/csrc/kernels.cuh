@@ -158,7 +158,9 @@ void launch_solve_kl(int method, double* X, const double* Yr, const TA* A, const
 // Y32 is the fp32 row-major copy of the fixed factor ([k][len], launch_factor_rows_f32); see the file header for the design.
 bool solve_kl_fast_supported(int k, int64_t len);
 void launch_factor_rows_f32(const double* Y, int k, int64_t len, float* out, cudaStream_t st);
-void launch_solve_kl_fast(int method, double* X, const float* Y32, const float* A, const double* sumY, const uint8_t* mask, int k,
+// WH0 (nullable): len x ncol fp32, the product Y' X of the factors the solve starts from (launch_product_tc)
+void launch_solve_kl_fast(int method, double* X, const float* Y32, const float* A, const float* WH0, const double* sumY,
+                          const uint8_t* mask, int k,
                           int64_t len, int64_t ncol, const double* pen, unsigned max_iter, double rel_tol,
                           unsigned long long* sweeps, cudaStream_t st);
 
@@ -187,6 +189,9 @@ void launch_split_rows(const double* X, int k, int64_t cols, __half* hi, __half*
 // out[0] = sum (A - W'H)^2, out[1] = sum (A+e) g((W'H - A) / (A+e)) over the finite entries (see the file header)
 void launch_error_tc(const float* A, int64_t n, int64_t m, int k, const __half* w_hi, const __half* w_lo, const float* rsw,
                      const __half* h_hi, const __half* h_lo, const float* rsh, double* part, double* out, cudaStream_t st);
+// out[i + n * j] = sum_c W[c, i] H[c, j] in fp32 from the same planes
+void launch_product_tc(int64_t n, int64_t m, int k, const __half* w_hi, const __half* w_lo, const float* rsw, const __half* h_hi,
+                       const __half* h_lo, const float* rsh, float* out, cudaStream_t st);
 void launch_factor_stats(const double* X, int k, int64_t cols, double* part, double* out, cudaStream_t st);
 
 }  // namespace nnlm

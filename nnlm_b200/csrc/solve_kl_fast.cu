@@ -44,7 +44,8 @@ void launch_factor_rows_f32(const double* Y, int k, int64_t len, float* out, cud
     NNLM_LAUNCHED();
 }
 
-void launch_solve_kl_fast(int method, double* X, const float* Y32, const float* A, const double* sumY, const uint8_t* mask, int k,
+void launch_solve_kl_fast(int method, double* X, const float* Y32, const float* A, const float* WH0, const double* sumY,
+                          const uint8_t* mask, int k,
                           int64_t len, int64_t ncol, const double* pen, unsigned max_iter, double rel_tol,
                           unsigned long long* sweeps, cudaStream_t st)
 {

@@ -144,8 +144,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 template <int METHOD, int E>
 __global__ void __launch_bounds__(KLF_NT, 1)
-k_solve_kl_fast(double* __restrict__ X, const float* __restrict__ Y32, const float* __restrict__ A, const double* __restrict__ sumY,
-                const uint8_t* __restrict__ mask, int k, int64_t len, int64_t ncol, double b0, double b1, double b2,
+k_solve_kl_fast(double* __restrict__ X, const float* __restrict__ Y32, const float* __restrict__ A, const float* __restrict__ WH0,
+                const double* __restrict__ sumY, const uint8_t* __restrict__ mask, int k, int64_t len, int64_t ncol, double b0, double b1, double b2,
                 unsigned max_iter, double rel_tol, unsigned long long* __restrict__ sweeps)
 {
     cg::cluster_group cluster = cg::this_cluster();
@@ -248,6 +248,16 @@ k_solve_kl_fast(double* __restrict__ X, const float* __restrict__ Y32, const flo
         for (int e = 0; e < E; e++)
 #pragma unroll
             for (int j = 0; j < KLF_J; j++) wh[e][j] = 0.0f;
+        if (WH0 != nullptr) {
+            // the product was formed on the tensor cores (error_tc.cu, launch_product_tc): one coalesced load per entry
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                const int64_t i = i_first + (int64_t)e * stride;
+#pragma unroll
+                for (int j = 0; j < KLF_J; j++)
+                    wh[e][j] = (((valid >> e) & 1u) && col0 + j < ncol) ? __ldg(WH0 + i + len * (col0 + j)) : 0.0f;
+            }
+        } else
         // (rows straight from L2 into registers, two to four rows = up to 26 loads in flight per thread: staged one row ahead through shared
         // memory like the sweeps below, every coordinate paid the full L2 latency — this loop was 60 % of the H-half at config 3)
         {
@@ -484,7 +494,7 @@ inline bool klf_shape(int64_t len, KlfShape* out)
 }
 
 template <int METHOD, int E>
-void launch_e(const KlfShape& sh, double* X, const float* Y32, const float* A, const double* sumY, const uint8_t* mask, int k,
+void launch_e(const KlfShape& sh, double* X, const float* Y32, const float* A, const float* WH0, const double* sumY, const uint8_t* mask, int k,
               int64_t len, int64_t ncol, const double* pen, unsigned max_iter, double rel_tol, unsigned long long* sweeps,
               cudaStream_t st)
 {
@@ -512,28 +522,28 @@ void launch_e(const KlfShape& sh, double* X, const float* Y32, const float* A, c
     }
     const int64_t clusters = std::max<int64_t>(1, std::min<int64_t>(groups, std::min<int64_t>(res, 148 / sh.S)));
     cfg.gridDim = dim3((unsigned)(clusters * sh.S));
-    NNLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, X, Y32, A, sumY, mask, k, len, ncol, pen[0], pen[1], pen[2], max_iter, rel_tol, sweeps));
+    NNLM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, X, Y32, A, WH0, sumY, mask, k, len, ncol, pen[0], pen[1], pen[2], max_iter, rel_tol, sweeps));
     NNLM_LAUNCHED();
 }
 
 template <int METHOD, int E0>
-void launch_range(const KlfShape& sh, double* X, const float* Y32, const float* A, const double* sumY, const uint8_t* mask, int k,
+void launch_range(const KlfShape& sh, double* X, const float* Y32, const float* A, const float* WH0, const double* sumY, const uint8_t* mask, int k,
                   int64_t len, int64_t ncol, const double* pen, unsigned max_iter, double rel_tol, unsigned long long* sweeps,
                   cudaStream_t st)
 {
     // E0 .. E0 + 3
     switch (sh.E - E0) {
-        case 0: launch_e<METHOD, E0>(sh, X, Y32, A, sumY, mask, k, len, ncol, pen, max_iter, rel_tol, sweeps, st); break;
-        case 1: launch_e<METHOD, E0 + 1>(sh, X, Y32, A, sumY, mask, k, len, ncol, pen, max_iter, rel_tol, sweeps, st); break;
-        case 2: launch_e<METHOD, E0 + 2>(sh, X, Y32, A, sumY, mask, k, len, ncol, pen, max_iter, rel_tol, sweeps, st); break;
-        default: launch_e<METHOD, E0 + 3>(sh, X, Y32, A, sumY, mask, k, len, ncol, pen, max_iter, rel_tol, sweeps, st); break;
+        case 0: launch_e<METHOD, E0>(sh, X, Y32, A, WH0, sumY, mask, k, len, ncol, pen, max_iter, rel_tol, sweeps, st); break;
+        case 1: launch_e<METHOD, E0 + 1>(sh, X, Y32, A, WH0, sumY, mask, k, len, ncol, pen, max_iter, rel_tol, sweeps, st); break;
+        case 2: launch_e<METHOD, E0 + 2>(sh, X, Y32, A, WH0, sumY, mask, k, len, ncol, pen, max_iter, rel_tol, sweeps, st); break;
+        default: launch_e<METHOD, E0 + 3>(sh, X, Y32, A, WH0, sumY, mask, k, len, ncol, pen, max_iter, rel_tol, sweeps, st); break;
     }
 }
 
 
-#define NNLM_KLF_ARGS const KlfShape& sh, double* X, const float* Y32, const float* A, const double* sumY, const uint8_t* mask, int k, \
+#define NNLM_KLF_ARGS const KlfShape& sh, double* X, const float* Y32, const float* A, const float* WH0, const double* sumY, const uint8_t* mask, int k, \
     int64_t len, int64_t ncol, const double* pen, unsigned max_iter, double rel_tol, unsigned long long* sweeps, cudaStream_t st
-#define NNLM_KLF_PASS sh, X, Y32, A, sumY, mask, k, len, ncol, pen, max_iter, rel_tol, sweeps, st
+#define NNLM_KLF_PASS sh, X, Y32, A, WH0, sumY, mask, k, len, ncol, pen, max_iter, rel_tol, sweeps, st
 // explicit-instantiation entry points, one translation unit each (build parallelism): method x entries-per-thread range
 void launch_m3_lo(NNLM_KLF_ARGS);   // method 3, E 1..8
 void launch_m3_hi(NNLM_KLF_ARGS);   // method 3, E 9..16
