@@ -687,12 +687,12 @@ CrossPlan cross_tc_plan(int k, int64_t len, int64_t ncol, bool pairs)
 }
 
 void launch_cross_tc(const CrossPlan& plan, const __half* a_hi, const __half* a_lo, const __half* f_hi, const __half* f_lo,
-                     const double* unscale, const double* center, const double* fsum, double* Qp, cudaStream_t st)
+                     const double* unscale, const double* center, const double* fsum, double* Qp, cudaStream_t st, int drain)
 {
     NNLM_REQUIRE(cross_tc_supported(plan.k), "tensor-core cross-product supports rank k <= 128");
-    if (plan.np == 32)      launch_np<32, 5, 0>(plan, a_hi, a_lo, f_hi, f_lo, unscale, center, fsum, Qp, 0, st);
-    else if (plan.np == 64) launch_np<64, 4, 0>(plan, a_hi, a_lo, f_hi, f_lo, unscale, center, fsum, Qp, 0, st);
-    else                    launch_np<128, 3, 0>(plan, a_hi, a_lo, f_hi, f_lo, unscale, center, fsum, Qp, 0, st);
+    if (plan.np == 32)      launch_np<32, 5, 0>(plan, a_hi, a_lo, f_hi, f_lo, unscale, center, fsum, Qp, drain, st);
+    else if (plan.np == 64) launch_np<64, 4, 0>(plan, a_hi, a_lo, f_hi, f_lo, unscale, center, fsum, Qp, drain, st);
+    else                    launch_np<128, 3, 0>(plan, a_hi, a_lo, f_hi, f_lo, unscale, center, fsum, Qp, drain, st);
 }
 
 // Exact contraction of two integer-valued fp16 planes (MODE 1): Qp[slot][ncol][128] = unscale[a] * sum_i f[a,i] * a[i,j].

@@ -464,8 +464,11 @@ void Engine::run_half_tc(const Half& h)
                            reinterpret_cast<unsigned int*>(tpc_scratch_.p) + 1, sumY_.p, fscales_.p, unscale_.p, f_hi_.p, f_lo_.p, st_);
         timer.end(st_);
         timer.begin(KernelTimer::CROSS, st_);
+        // NA path: the per-column Grams of a near-rank-one factor amplify the cross-product's error ~750x at config 4's size
+        // (T = 1 from the tiny init: rel H 1.55e-5 against the oracle with 256 indices per TMEM accumulation, scratch/na_t1_full.py),
+        // and the cross-product is 3 % of that path's time: it drains every 64 indices there
         launch_cross_tc(plan, h.w_side ? t_hi_.p : a_hi_.p, h.w_side ? t_lo_.p : a_lo_.p, f_hi_.p, f_lo_.p, unscale_.p,
-                        h.w_side ? rowmean_.p : colmean_.p, sumY_.p, Qp_.p, st_);
+                        h.w_side ? rowmean_.p : colmean_.p, sumY_.p, Qp_.p, st_, missing ? 1 : 0);
         timer.end(st_);
     }
     if (!missing) { solve_dense_ls(h, plan.slots); return; }

@@ -74,9 +74,10 @@ CrossPlan cross_tc_plan(int k, int64_t len, int64_t ncol, bool pairs = false);
 // Qp[slot][ncol][k] (slots = plan.slots, zero-filled here) = partial cross-products; sum over slots = F * A.
 // a_* : planes of the A copy of this half (row j = column j of the matrix, pitch plan.ld_a); f_* : planes of the factor.
 // center[ncol] = the per-column mean that was subtracted from A before the split, fsum[k] = rowSums(F): the mean component
-// center[j]*fsum[a] is added back in fp64 (slot 0).
+// center[j]*fsum[a] is added back in fp64 (slot 0). drain: k-blocks of 64 indices per fp32 TMEM accumulation (0 = the default
+// of the tile width: 4 for k <= 64, 1 above).
 void launch_cross_tc(const CrossPlan& plan, const __half* a_hi, const __half* a_lo, const __half* f_hi, const __half* f_lo,
-                     const double* unscale, const double* center, const double* fsum, double* Qp, cudaStream_t st);
+                     const double* unscale, const double* center, const double* fsum, double* Qp, cudaStream_t st, int drain = 0);
 // means over the finite entries of the columns (ncol values) and rows (len values, nullptr to skip) of A
 void launch_means(const double* A, int64_t len, int64_t ncol, double* colmean, double* rowmean, cudaStream_t st);
 // maxbits[0] = bit pattern of max |A| over the finite entries (a u64: non-negative doubles order like integers, so shards

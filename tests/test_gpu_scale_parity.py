@@ -164,6 +164,38 @@ def test_first_iteration_missing_config4_shape():
     np.testing.assert_allclose(got.mse, ref["mse"], rtol=1e-6)
 
 
+def test_first_iteration_missing_config4_full_size():
+    """T = 1 of config 4 at its FULL size (50000 x 10000, 20 % NA, k = 50) against the oracle. The per-column Grams of the near
+    rank-one first W amplify the cross-product's error ~750x at this size (not at 5000 x 2000): with 256 indices per fp32 TMEM
+    accumulation the fast path was 1.55e-5 off on H; it drains every 64 indices on the NA path since (measured 1.4e-6).
+    One oracle iteration costs ~20 s on 16 cores: skipped on small hosts."""
+    cores = oracle.host_cores()
+    if cores < 8:
+        pytest.skip(f"the full-size oracle iteration needs >= 8 host cores ({cores} here)")
+    from nnlm_b200.session import Session
+    n, m, k = 50000, 10000, 50
+    W0 = 0.01 * oracle.splitmix_uniform(11, n * k).reshape((n, k), order="F")
+    H0 = 0.01 * oracle.splitmix_uniform(12, k * m).reshape((k, m), order="F")
+    s = Session(k=k, method=1, inner_max_iter=50, inner_rel_tol=1e-9, precision=K.PREC_FAST, device=0,
+                synthetic=dict(n=n, m=m, na_frac=0.2))
+    s.set_factors(W0, H0)
+    s.run(1)
+    Wg, Hg = s.get_factors()
+    s.close()
+    oracle.set_threads(cores)
+    A = oracle.synth_matrix(n, m, k, na_frac=0.2)          # bit-identical twin of the device generator
+    At = oracle.transpose(A)
+    kw = dict(n_threads=0, method=1, max_iter=50, rel_tol=1e-9, with_missing=1)
+    Wt, _ = oracle.update(np.asfortranarray(W0.T), H0.copy(order="F"), At, **kw)
+    del At
+    Ho, _ = oracle.update(H0.copy(order="F"), Wt, A, **kw)
+    del A
+    ew, eh = rel(Wg, np.asfortranarray(Wt.T)), rel(Hg, Ho)
+    worst = float((np.linalg.norm(Hg - Ho, axis=0) / np.maximum(np.linalg.norm(Ho, axis=0), 1e-300)).max())
+    print(f"config 4 full size T=1: rel W {ew:.2e}, rel H {eh:.2e}, worst column of H {worst:.2e}")
+    assert ew < TOL and eh < TOL
+
+
 def heavy_tailed(n, m, seed=7):
     """Count-like data: a lognormal body with one huge entry. max/rms is bounded by sqrt(n m) (a single spike), so the
     matrix has to be large to reach 1e4: 20000 x 6000 with the spike at 2e5."""
