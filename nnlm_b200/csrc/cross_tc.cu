@@ -63,6 +63,7 @@ struct CrossParams {
     const double* unscale; // [NP]: 1 / (s_A * s_F[a])
     int drain;             // k-blocks accumulated in TMEM between two drains into the fp64 registers
     int d1_every;          // drains of the large-term accumulator per drain of the small-term one (MODE 0; 1 otherwise)
+    int halves;            // 2: every k-block is drained twice, after 32 indices each (needs drain == 1); else 1
     const double* center;  // [ncol] mean of each column of A that was subtracted before the split (or nullptr)
     const double* fsum;    // [k] row sums of the factor
 };
@@ -155,6 +156,38 @@ k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ 
                 const int64_t tile = u / KBn;
                 const int64_t seg_end = min(u1, (tile + 1) * KBn);
                 uint32_t sub = 0;
+                while (p.halves == 2 && u < seg_end) {            // 32 contraction indices per fp32 accumulation: two chunks per k-block
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(tiles + stage * STAGE_BYTES);
+                    const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + A_BYTES);
+                    const uint64_t f_hi = make_desc(sa + (MODE == 0 ? 2 * A_BYTES : A_BYTES));
+                    const uint64_t f_lo = make_desc(sa + (MODE == 0 ? 2 * A_BYTES + F_BYTES : A_BYTES + F_BYTES));
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        const uint32_t buf = chunk & 1, tph = (chunk >> 1) & 1;
+                        mbar_wait(&tempty[buf], tph ^ 1);
+                        tc_fence_after();
+                        const bool big_first = (sub % (uint32_t)p.d1_every) == 0;
+                        if (big_first) cur_big = big++;
+                        const uint32_t d0 = tmem_base + buf * NP, d1 = tmem_base + 2 * NP + (cur_big & 1) * NP;
+#pragma unroll
+                        for (int ks = 2 * hh; ks < 2 * hh + 2; ks++) {
+                            const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+                            const uint32_t acc = (ks == 2 * hh) ? 0u : 1u;
+                            const uint32_t acc1 = (ks == 2 * hh && big_first) ? 0u : 1u;
+                            umma_f16(d0, a_hi + adv, f_hi + adv, IDESC, acc);
+                            if (MODE != 1) umma_f16(d1, a_hi + adv, f_lo + adv, IDESC, acc1);
+                            if (MODE == 0) umma_f16(d1, a_lo + adv, f_hi + adv, IDESC, 1u);
+                        }
+                        if (hh == 1) tc_commit(&empty[stage]);
+                        tc_commit(&tfull[buf]);
+                        chunk++;
+                        sub++;
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    u++;
+                }
                 while (u < seg_end) {
                     const int64_t chunk_end = min(seg_end, u + (int64_t)p.drain);
                     const uint32_t buf = chunk & 1, tph = (chunk >> 1) & 1;
@@ -209,12 +242,15 @@ k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ 
 #pragma unroll
             for (int c = 0; c < CPT; c++) acc[c] = 0.0;
             uint32_t sub = 0;
+            int hh = 0;                                 // p.halves == 2: which half of the k-block this chunk is
             while (u < seg_end) {
-                const int64_t chunk_end = min(seg_end, u + (int64_t)p.drain);
+                const bool half_mode = p.halves == 2;
+                const int64_t chunk_end = half_mode ? u + 1 : min(seg_end, u + (int64_t)p.drain);
+                const bool closes_kblock = !half_mode || hh == 1;
                 const uint32_t buf = chunk & 1, tph = (chunk >> 1) & 1;
                 if ((sub % (uint32_t)p.d1_every) == 0) cur_big = big++;
                 // the small-term accumulator is read with the last drain chunk of its group (or of the tile)
-                const bool with_d1 = MODE != 1 && (chunk_end == seg_end || ((sub + 1) % (uint32_t)p.d1_every) == 0);
+                const bool with_d1 = MODE != 1 && ((closes_kblock && chunk_end == seg_end) || ((sub + 1) % (uint32_t)p.d1_every) == 0);
                 mbar_wait(&tfull[buf], tph);
                 tc_fence_after();
                 constexpr int CH = CPT > 32 ? 32 : CPT;          // TMEM columns read per tcgen05.ld
@@ -242,7 +278,7 @@ k_cross_tc(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ 
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[buf]);           // buffer may be overwritten by the next-but-one chunk
-                u = chunk_end;
+                if (closes_kblock) { u = chunk_end; hh = 0; } else hh = 1;
                 chunk++;
                 sub++;
             }
@@ -650,7 +686,12 @@ void launch_np(const CrossPlan& plan, const __half* a_hi, const __half* a_lo, co
     p.drain = drain > 0 ? drain : (drain_env > 0 ? drain_env : (NP >= 128 ? DRAIN_LARGE : DRAIN_SMALL));
     // the hi*lo + lo*hi accumulator is 2^-11 of the hi*hi one: its fp32 truncation matters 2^-11 as much, so it keeps
     // round 1's 1024 indices per drain and the epilogue converts half as many values on the other drains
-    p.d1_every = MODE == 0 ? std::max(1, 16 / p.drain) : 1;
+    // NNLM_TC_HALVES=2 (experiment): 32 indices per accumulation for NP = 128, two chunks per k-block. Measured at config 5's full
+    // size (scratch/c5_t1_full.py): T = 1 rel H 1.26e-5 with 64 indices AND with 32 (rel W 4.1e-9 -> 3.6e-9), at -10 % speed — what
+    // is left there is the 22-24-bit storage of A itself (the oracle run on fp32-rounded A moves as much), so the default stays 1.
+    static const int halves_env = [] { const char* e = getenv("NNLM_TC_HALVES"); return e ? atoi(e) : 0; }();
+    p.halves = (MODE == 0 && NP >= 128 && p.drain == 1 && halves_env == 2) ? 2 : 1;
+    p.d1_every = MODE == 0 ? std::max(1, 16 * p.halves / p.drain) : 1;
     p.center = center; p.fsum = fsum;
     kern<<<plan.grid, THREADS, smem, st>>>(mA_hi, mA_lo, mF_hi, mF_lo, p);
     NNLM_LAUNCHED();
@@ -725,7 +766,7 @@ void launch_mask_tc2(const CrossPlan& plan, const __half* a_plane, const __half*
     const CUtensorMap mF1 = make_map(f1, plan.len, 128, plan.ld_f, 128);
     CrossParams p;
     p.ncol = plan.ncol; p.kblocks = plan.kblocks; p.units = plan.units; p.k = plan.k; p.slots = plan.slots; p.Qp = Qp; p.unscale = unscale;
-    p.drain = 64; p.d1_every = 1; p.center = nullptr; p.fsum = nullptr;
+    p.drain = 64; p.d1_every = 1; p.halves = 1; p.center = nullptr; p.fsum = nullptr;
     k_mask_tc2<<<2 * plan.grid, THREADS, smem, st>>>(mA, mF0, mF1, p);
     NNLM_LAUNCHED();
 }
